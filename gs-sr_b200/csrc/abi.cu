@@ -1,0 +1,259 @@
+// abi.cu -- extern "C" entry points of libgsr_b200.so (see include/gsr_b200.h)
+// and the host-side orchestration of the surfel pipeline.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include "common.cuh"
+#include "../../include/gsr_b200.h"
+
+namespace gsr {
+
+// ---- kernels / helpers defined in the other translation units ---------------
+__global__ void surfel_preprocess_fwd(int, int, int, const float*, const float2*, const float4*, const float*,
+                                      const float*, const float*, const bool, const ViewParams, const bool,
+                                      const bool, int*, GeomRec*, float4*, uint32_t*, float*, uint8_t*, int*);
+__global__ void surfel_preprocess_bwd(int, int, int, const float*, const float2*, const float4*, const float*,
+                                      const bool, const ViewParams, const int, const int, const int*,
+                                      const GeomRec*, const uint8_t*, const float*, float*, float*, float*,
+                                      float*, float*, float*, float*, float*, float*);
+__global__ void mark_visible_kernel(int, const float*, const ViewParams, uint8_t*);
+__global__ void duplicate_with_keys(int, const GeomRec*, const int*, const uint32_t*, int, int, uint64_t*,
+                                    uint32_t*);
+__global__ void build_records(int, const uint64_t*, const uint32_t*, const GeomRec*, const float4*,
+                              const float*, int, SplatRec*, uint2*);
+__global__ void surfel_render_fwd(const uint2*, const SplatRec*, int, int, int, const float*, float*,
+                                  uint32_t*, float*, float*);
+__global__ void surfel_render_bwd(const uint2*, const SplatRec*, int, int, int, const float*,
+                                  const float*, const uint32_t*, const float*, const float*, float*);
+size_t scan_temp_bytes(int P);
+cudaError_t inclusive_scan(char*, size_t, const uint32_t*, uint32_t*, int, cudaStream_t);
+size_t sort_temp_bytes(int64_t R);
+cudaError_t sort_pairs(char*, size_t, const uint64_t*, uint64_t*, const uint32_t*, uint32_t*, int64_t, int,
+                       cudaStream_t);
+
+// ---- error string -------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- workspace layouts ----------------------------------------------------------
+size_t GeomWs::carve(GeomWs& w, char* base, int P, size_t scan_bytes) {
+    Carver c(base);
+    size_t n = P > 0 ? (size_t)P : 1;
+    w.geom = c.take<GeomRec>(n);
+    w.cbox = c.take<float4>(n);
+    w.tiles = c.take<uint32_t>(n);
+    w.offsets = c.take<uint32_t>(n);
+    w.rgb = c.take<float>(3 * n);
+    w.clamped = c.take<uint8_t>(3 * n);
+    w.flags = c.take<int>(32);
+    w.scan_tmp = c.take<char>(scan_bytes);
+    w.scan_tmp_bytes = scan_bytes;
+    return c.used + 256;
+}
+size_t ImageWs::carve(ImageWs& w, char* base, int W, int H) {
+    Carver c(base);
+    size_t N = (size_t)W * H;
+    size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    w.final_T = c.take<float>(3 * N);
+    w.n_contrib = c.take<uint32_t>(2 * N);
+    w.ranges = c.take<uint2>(tiles);
+    return c.used + 256;
+}
+size_t BinWs::carve(BinWs& w, char* base, int64_t R, int P, size_t sort_bytes) {
+    Carver c(base);
+    size_t n = R > 0 ? (size_t)R : 1;
+    w.keys_unsorted = c.take<uint64_t>(n);
+    w.keys = c.take<uint64_t>(n);
+    w.vals_unsorted = c.take<uint32_t>(n);
+    w.vals = c.take<uint32_t>(n);
+    w.recs = c.take<SplatRec>(n);
+    w.gacc = c.take<float>((size_t)(P > 0 ? P : 1) * GACC_STRIDE);
+    w.sort_tmp = c.take<char>(sort_bytes);
+    w.sort_tmp_bytes = sort_bytes;
+    return c.used + 256;
+}
+
+static inline char* align256(char* p) {
+    return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255));
+}
+
+static uint32_t ceil_log2_tiles(uint32_t n) {  // bits needed for tile ids 0..n-1 (>= reference's getHigherMsb)
+    uint32_t b = 0;
+    while ((1ull << b) < (unsigned long long)n) b++;
+    return b ? b : 1;
+}
+
+static ViewParams make_view(const float* view, const float* proj, const float* campos, int W, int H,
+                            float scale_modifier) {
+    ViewParams vc;
+    vc.view = view; vc.proj = proj; vc.campos = campos;
+    vc.W = W; vc.H = H;
+    vc.gx = (W + TILE - 1) / TILE; vc.gy = (H + TILE - 1) / TILE;
+    vc.scale_modifier = scale_modifier;
+    return vc;
+}
+
+static bool no_cull_env() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GSR_NO_CULL"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+const char* gsr_last_error(void) { return g_err; }
+const char* gsr_build_arch(void) { return "sm_100a"; }
+
+int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer, gsr_buffer_fn imageBuffer,
+                       void* user, int P, int D, int M, const float* background, int width, int height,
+                       const float* means3D, const float* shs, const float* colors_precomp,
+                       const float* opacities, const float* scales, float scale_modifier,
+                       const float* rotations, const float* transMat_precomp, const float* viewmatrix,
+                       const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                       int prefiltered, float* out_color, float* out_others, int* radii, int debug,
+                       void* stream_v) {
+    (void)tan_fovx; (void)tan_fovy;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    if (P < 0 || width <= 0 || height <= 0 || !out_color || !out_others || !background || !viewmatrix ||
+        !projmatrix) { set_error("gsr_surfel_forward: invalid argument"); return GSR_E_INVALID; }
+    if (P > 0 && (!means3D || !opacities || !radii)) { set_error("gsr_surfel_forward: means3D/opacities/radii required"); return GSR_E_INVALID; }
+    if (P > 0 && ((shs == nullptr) == (colors_precomp == nullptr))) { set_error("provide exactly one of shs / colors_precomp"); return GSR_E_INVALID; }
+    if (P > 0 && (((scales == nullptr) || (rotations == nullptr)) == (transMat_precomp == nullptr))) { set_error("provide exactly one of scales+rotations / transMat_precomp"); return GSR_E_INVALID; }
+    if (P > 0 && shs && !cam_pos) { set_error("cam_pos required with shs"); return GSR_E_INVALID; }
+    const int W = width, H = height;
+    const size_t N = (size_t)W * H;
+
+    const ViewParams vc = make_view(viewmatrix, projmatrix, cam_pos, W, H, scale_modifier);
+    const int ntiles = vc.gx * vc.gy;
+
+    ImageWs iw;
+    size_t ibytes = ImageWs::carve(iw, nullptr, W, H);
+    char* ibase = imageBuffer(user, ibytes);
+    if (!ibase) { set_error("imageBuffer callback failed (%zu bytes)", ibytes); return GSR_E_ALLOC; }
+    ImageWs::carve(iw, align256(ibase), W, H);
+    GSR_CUDA_CHECK(cudaMemsetAsync(iw.ranges, 0, (size_t)ntiles * sizeof(uint2), s));
+
+    int R = 0;
+    GeomWs gw;
+    BinWs bw;
+    memset(&bw, 0, sizeof(bw));
+    if (P > 0) {
+        size_t scan_bytes = scan_temp_bytes(P);
+        size_t gbytes = GeomWs::carve(gw, nullptr, P, scan_bytes);
+        char* gbase = geometryBuffer(user, gbytes);
+        if (!gbase) { set_error("geometryBuffer callback failed (%zu bytes)", gbytes); return GSR_E_ALLOC; }
+        GeomWs::carve(gw, align256(gbase), P, scan_bytes);
+        GSR_CUDA_CHECK(cudaMemsetAsync(gw.flags, 0, 32 * sizeof(int), s));
+
+        surfel_preprocess_fwd<<<(P + 255) / 256, 256, 0, s>>>(
+            P, D, M, means3D, (const float2*)scales, (const float4*)rotations, opacities, shs, transMat_precomp,
+            colors_precomp != nullptr, vc, prefiltered != 0, no_cull_env(), radii, gw.geom, gw.cbox, gw.tiles,
+            gw.rgb, gw.clamped, gw.flags);
+        GSR_CUDA_CHECK(cudaGetLastError());
+        GSR_CUDA_CHECK(inclusive_scan(gw.scan_tmp, gw.scan_tmp_bytes, gw.tiles, gw.offsets, P, s));
+        // num_rendered sizes the binning buffer: same single read-back as the reference
+        // (S/rasterizer_impl.cu:282), plus the prefiltered flag.
+        uint32_t Ru = 0;
+        int flag = 0;
+        GSR_CUDA_CHECK(cudaMemcpyAsync(&Ru, gw.offsets + (P - 1), 4, cudaMemcpyDeviceToHost, s));
+        GSR_CUDA_CHECK(cudaMemcpyAsync(&flag, gw.flags, 4, cudaMemcpyDeviceToHost, s));
+        GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (flag) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
+        if (Ru > 0x7fffff00u) { set_error("num_rendered overflow (%u)", Ru); return GSR_E_OVERFLOW; }
+        R = (int)Ru;
+    }
+
+    size_t sort_bytes = R > 0 ? sort_temp_bytes(R) : 0;
+    size_t bbytes = BinWs::carve(bw, nullptr, R, P, sort_bytes);
+    char* bbase = binningBuffer(user, bbytes);
+    if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
+    BinWs::carve(bw, align256(bbase), R, P, sort_bytes);
+
+    if (R > 0) {
+        duplicate_with_keys<<<(P + 255) / 256, 256, 0, s>>>(P, gw.geom, radii, gw.offsets, vc.gx, vc.gy,
+                                                            bw.keys_unsorted, bw.vals_unsorted);
+        GSR_CUDA_CHECK(cudaGetLastError());
+        int end_bit = 32 + (int)ceil_log2_tiles((uint32_t)ntiles);
+        GSR_CUDA_CHECK(sort_pairs(bw.sort_tmp, bw.sort_tmp_bytes, bw.keys_unsorted, bw.keys, bw.vals_unsorted,
+                                  bw.vals, R, end_bit, s));
+        const float* colors = colors_precomp ? colors_precomp : gw.rgb;
+        build_records<<<(R + 255) / 256, 256, 0, s>>>(R, bw.keys, bw.vals, gw.geom, gw.cbox, colors, vc.gx,
+                                                      bw.recs, iw.ranges);
+        GSR_CUDA_CHECK(cudaGetLastError());
+    }
+    surfel_render_fwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.recs, W, H, vc.gx, background,
+                                                  iw.final_T, iw.n_contrib, out_color, out_others);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    (void)N;
+    if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return R;
+}
+
+int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                        const float* means3D, const float* shs, const float* colors_precomp,
+                        const float* scales, float scale_modifier, const float* rotations,
+                        const float* transMat_precomp, const float* viewmatrix, const float* projmatrix,
+                        const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                        char* geom_buffer, char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                        const float* dL_dothers, float* dL_dmean2D, float* dL_dnormal, float* dL_dopacity,
+                        float* dL_dcolor, float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh,
+                        float* dL_dscale, float* dL_drot, int debug, void* stream_v) {
+    (void)colors_precomp;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    if (P == 0) return GSR_OK;
+    if (P < 0 || R < 0 || !geom_buffer || !binning_buffer || !image_buffer || !dL_dpix || !dL_dothers ||
+        !dL_dmean2D || !dL_dnormal || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dtransMat || !radii ||
+        !means3D) { set_error("gsr_surfel_backward: invalid argument"); return GSR_E_INVALID; }
+    if (M > 0 && shs && !dL_dsh) { set_error("dL_dsh required with shs"); return GSR_E_INVALID; }
+    const int W = width, H = height;
+    // S/backward.cu:614-615: W,H recomputed from float32 focal * tan * 2 and truncated (quirk Q3)
+    const float focal_y = (float)H / (2.0f * tan_fovy), focal_x = (float)W / (2.0f * tan_fovx);
+    const int Wb = (int)(focal_x * tan_fovx * 2), Hb = (int)(focal_y * tan_fovy * 2);
+    const ViewParams vc = make_view(viewmatrix, projmatrix, campos, W, H, scale_modifier);
+    const int ntiles = vc.gx * vc.gy;
+
+    GeomWs gw; ImageWs iw; BinWs bw;
+    GeomWs::carve(gw, align256(geom_buffer), P, scan_temp_bytes(P));
+    ImageWs::carve(iw, align256(image_buffer), W, H);
+    BinWs::carve(bw, align256(binning_buffer), R, P, R > 0 ? sort_temp_bytes(R) : 0);
+
+    GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * GACC_STRIDE * sizeof(float), s));
+    if (R > 0) {
+        surfel_render_bwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.recs, W, H, vc.gx, background,
+                                                      iw.final_T, iw.n_contrib, dL_dpix, dL_dothers,
+                                                      bw.gacc);
+        GSR_CUDA_CHECK(cudaGetLastError());
+    }
+    const bool precomp = (scales == nullptr);
+    surfel_preprocess_bwd<<<(P + 255) / 256, 256, 0, s>>>(
+        P, D, M, means3D, (const float2*)scales, (const float4*)rotations, shs, precomp, vc, Wb, Hb, radii,
+        gw.geom, gw.clamped, bw.gacc, dL_dmean2D, dL_dnormal, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat,
+        shs ? dL_dsh : nullptr, dL_dscale, dL_drot);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return GSR_OK;
+}
+
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream_v) {
+    (void)projmatrix;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    if (P == 0) return GSR_OK;
+    if (P < 0 || !means3D || !viewmatrix || !present) { set_error("gsr_mark_visible: invalid argument"); return GSR_E_INVALID; }
+    const ViewParams vc = make_view(viewmatrix, projmatrix, nullptr, 0, 0, 1.0f);
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, vc, present);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    return GSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// surfel_preprocess.cu -- per-Gaussian forward / backward preprocess of the 2DGS
+// surfel rasterizer for sm_100a.
+//
+// Semantics follow the reference kernels
+//   forward : S/cuda_rasterizer/forward.cu:148-251 (+ compute_transmat :75-115,
+//             compute_aabb :119-145, computeColorFromSH :20-71)
+//   backward: S/cuda_rasterizer/backward.cu:582-637 (+ compute_transmat_aabb :450-580,
+//             computeColorFromSH :20-139)
+// but the data layout is ours: the forward emits one 64-byte GeomRec per
+// Gaussian (four 128-bit stores) plus a conservative contribution box used to
+// cull (pixel, splat) pairs without changing any result; the backward reads
+// the reduced 80-byte gradient accumulator and fully writes every output
+// (zeros for culled Gaussians), so no output needs a memset.
+#include "common.cuh"
+#include "sh.cuh"
+#include "../../include/gsr_b200.h"
+
+namespace gsr {
+
+__device__ __forceinline__ void load16(const float* __restrict__ src, float* dst) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) dst[i] = __ldg(src + i);
+}
+
+// quat (w,x,y,z) -> rotation columns, normalised in-kernel (S/auxiliary.h:215-237)
+__device__ __forceinline__ void quat_to_rot(float4 q, float3& c0, float3& c1, float3& c2) {
+    float s = rsqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
+    c0 = make_float3(1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y));
+    c1 = make_float3(2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x));
+    c2 = make_float3(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
+}
+
+// Conservative box (global pixel coords) outside of which alpha < 1/255 for sure.
+//   alpha = min(.99, o * exp(-rho/2)) >= 1/255  <=>  rho <= tau = 2 ln(255 o),
+//   rho = min(rho3d, rho2d): union of the disc |pix - c|^2 <= tau/2 around the filter
+//   centre and of the projected ellipse rho3d <= tau (same closed form as
+//   compute_aabb with cutoff^2 = tau).  When the tau-disc of the splat reaches
+//   the camera plane (d >= 0) the projection is not an ellipse: return "everything".
+__device__ __forceinline__ float4 contribution_box(float3 Tu, float3 Tv, float3 Tw, float cx,
+                                                   float cy, float opacity) {
+    const float BIG = 3.0e38f;
+    float a = 255.0f * opacity;
+    if (!(a >= 1.0f)) return make_float4(BIG, -BIG, BIG, -BIG);  // can never reach 1/255 (also NaN-safe: empty)
+    float tau = 2.0f * logf(a) * 1.001f + 1e-3f;                 // slack for float rounding of exp/log
+    float r2 = sqrtf(0.5f * tau);
+    float x0 = cx - r2, x1 = cx + r2, y0 = cy - r2, y1 = cy + r2;
+    float ww = Tw.z * Tw.z;
+    float d = tau * (Tw.x * Tw.x + Tw.y * Tw.y) - ww;
+    if (!(d < -1e-4f * ww)) return make_float4(-BIG, BIG, -BIG, BIG);
+    float inv = 1.0f / d;
+    float fx = tau * inv, fz = -inv;
+    float ex = fx * (Tu.x * Tw.x + Tu.y * Tw.y) + fz * Tu.z * Tw.z;
+    float ey = fx * (Tv.x * Tw.x + Tv.y * Tw.y) + fz * Tv.z * Tw.z;
+    float hx2 = ex * ex - (fx * (Tu.x * Tu.x + Tu.y * Tu.y) + fz * Tu.z * Tu.z);
+    float hy2 = ey * ey - (fx * (Tv.x * Tv.x + Tv.y * Tv.y) + fz * Tv.z * Tv.z);
+    if (!(hx2 >= 0.f) || !(hy2 >= 0.f) || !(fabsf(ex) < 1e9f) || !(fabsf(ey) < 1e9f))
+        return make_float4(-BIG, BIG, -BIG, BIG);
+    // relative slack for cancellation in h^2 (terms of magnitude e^2)
+    float hx = sqrtf(hx2 + 1e-4f * (ex * ex + 1.f)), hy = sqrtf(hy2 + 1e-4f * (ey * ey + 1.f));
+    x0 = fminf(x0, ex - hx); x1 = fmaxf(x1, ex + hx);
+    y0 = fminf(y0, ey - hy); y1 = fmaxf(y1, ey + hy);
+    const float m = 0.5f;  // half-pixel safety margin
+    return make_float4(x0 - m, x1 + m, y0 - m, y1 + m);
+}
+
+__global__ void __launch_bounds__(256)
+surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
+                      const float2* __restrict__ scales, const float4* __restrict__ rotations,
+                      const float* __restrict__ opacities, const float* __restrict__ shs,
+                      const float* __restrict__ transMat_precomp, const bool has_colors,
+                      const ViewParams vc, const bool prefiltered, const bool no_cull,
+                      int* __restrict__ radii, GeomRec* __restrict__ geom, float4* __restrict__ cbox,
+                      uint32_t* __restrict__ tiles, float* __restrict__ rgb,
+                      uint8_t* __restrict__ clamped, int* __restrict__ flags) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    int radius_out = 0;
+    uint32_t tiles_out = 0;
+    float view[16];
+    load16(vc.view, view);
+    do {
+        float3 p = make_float3(__ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1), __ldg(means3D + 3 * idx + 2));
+        float3 pv = xform43(view, p);
+        if (pv.z <= 0.2f) {  // in_frustum, S/auxiliary.h:187-212
+            if (prefiltered) atomicExch(flags, 1);
+            break;
+        }
+        float3 Tu, Tv, Tw, normal;
+        if (transMat_precomp == nullptr) {
+            float3 c0, c1, c2;
+            quat_to_rot(__ldg(rotations + idx), c0, c1, c2);
+            float2 sc = __ldg(scales + idx);
+            float su = vc.scale_modifier * sc.x, sv = vc.scale_modifier * sc.y;
+            float3 L0 = make_float3(c0.x * su, c0.y * su, c0.z * su);
+            float3 L1 = make_float3(c1.x * sv, c1.y * sv, c1.z * sv);
+            // T = (splat2world^T * world2ndc) * ndc2pix in the reference's association order
+            float pm[16];
+            load16(vc.proj, pm);
+            float hw = 0.5f * (float)vc.W, hwm = 0.5f * (float)(vc.W - 1);
+            float hh = 0.5f * (float)vc.H, hhm = 0.5f * (float)(vc.H - 1);
+            float cu[4], cv[4], cc[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                cu[c] = L0.x * pm[c] + L0.y * pm[4 + c] + L0.z * pm[8 + c];
+                cv[c] = L1.x * pm[c] + L1.y * pm[4 + c] + L1.z * pm[8 + c];
+                cc[c] = p.x * pm[c] + p.y * pm[4 + c] + p.z * pm[8 + c] + pm[12 + c];
+            }
+            Tu = make_float3(cu[0] * hw + cu[3] * hwm, cv[0] * hw + cv[3] * hwm, cc[0] * hw + cc[3] * hwm);
+            Tv = make_float3(cu[1] * hh + cu[3] * hhm, cv[1] * hh + cv[3] * hhm, cc[1] * hh + cc[3] * hhm);
+            Tw = make_float3(cu[3], cv[3], cc[3]);
+            normal = xformvec43(view, c2);
+        } else {
+            const float* t = transMat_precomp + 9 * (size_t)idx;
+            Tu = make_float3(__ldg(t + 0), __ldg(t + 1), __ldg(t + 2));
+            Tv = make_float3(__ldg(t + 3), __ldg(t + 4), __ldg(t + 5));
+            Tw = make_float3(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8));
+            normal = make_float3(0.f, 0.f, 1.f);
+        }
+        // DUAL_VISIABLE, S/forward.cu:209-214
+        float cosv = -(pv.x * normal.x + pv.y * normal.y + pv.z * normal.z);
+        if (cosv == 0.f) break;
+        float mult = cosv > 0.f ? 1.f : -1.f;
+        normal = make_float3(mult * normal.x, mult * normal.y, mult * normal.z);
+
+        // compute_aabb with cutoff 3, S/forward.cu:119-145,223-231
+        float d = 9.0f * Tw.x * Tw.x + 9.0f * Tw.y * Tw.y - Tw.z * Tw.z;
+        if (d == 0.0f) break;
+        float invd = 1.0f / d;
+        float f0 = invd * 9.0f, f2 = -invd;
+        float cx = f0 * Tu.x * Tw.x + f0 * Tu.y * Tw.y + f2 * Tu.z * Tw.z;
+        float cy = f0 * Tv.x * Tw.x + f0 * Tv.y * Tw.y + f2 * Tv.z * Tw.z;
+        float h0 = cx * cx - (f0 * Tu.x * Tu.x + f0 * Tu.y * Tu.y + f2 * Tu.z * Tu.z);
+        float h1 = cy * cy - (f0 * Tv.x * Tv.x + f0 * Tv.y * Tv.y + f2 * Tv.z * Tv.z);
+        float ex = sqrtf(fmaxf(1e-4f, h0)), ey = sqrtf(fmaxf(1e-4f, h1));
+        float radius = ceilf(fmaxf(fmaxf(ex, ey), 3.0f * FILTER_SIZE));
+        int ri = (int)radius;
+        int x0, y0, x1, y1;
+        get_rect(cx, cy, ri, vc.gx, vc.gy, x0, y0, x1, y1);
+        if ((x1 - x0) * (y1 - y0) == 0) break;
+
+        if (!has_colors) {
+            float3 c = sh_to_rgb(D, M, p, make_float3(__ldg(vc.campos), __ldg(vc.campos + 1), __ldg(vc.campos + 2)),
+                                 shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx);
+            rgb[3 * (size_t)idx + 0] = c.x; rgb[3 * (size_t)idx + 1] = c.y; rgb[3 * (size_t)idx + 2] = c.z;
+        }
+        float opa = __ldg(opacities + idx);
+        GeomRec g;
+        g.tu = make_float4(Tu.x, Tu.y, Tu.z, cx);
+        g.tv = make_float4(Tv.x, Tv.y, Tv.z, cy);
+        g.tw = make_float4(Tw.x, Tw.y, Tw.z, opa);
+        g.nd = make_float4(normal.x, normal.y, normal.z, pv.z);
+        geom[idx] = g;
+        cbox[idx] = no_cull ? make_float4(-3e38f, 3e38f, -3e38f, 3e38f) : contribution_box(Tu, Tv, Tw, cx, cy, opa);
+        radius_out = ri;
+        tiles_out = (uint32_t)((y1 - y0) * (x1 - x0));
+    } while (0);
+    radii[idx] = radius_out;
+    tiles[idx] = tiles_out;
+}
+
+// quat_to_rotmat_vjp, S/auxiliary.h:240-284. vR columns c0,c1,c2 (column-major).
+__device__ __forceinline__ float4 quat_vjp(float4 q, float3 v0, float3 v1, float3 v2) {
+    float s = rsqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    float w = q.x * s, x = q.y * s, y = q.z * s, z = q.w * s;
+    float4 r;
+    r.x = 2.f * (x * (v1.z - v2.y) + y * (v2.x - v0.z) + z * (v0.y - v1.x));
+    r.y = 2.f * (-2.f * x * (v1.y + v2.z) + y * (v0.y + v1.x) + z * (v0.z + v2.x) + w * (v1.z - v2.y));
+    r.z = 2.f * (x * (v0.y + v1.x) - 2.f * y * (v0.x + v2.z) + z * (v1.z + v2.y) + w * (v2.x - v0.z));
+    r.w = 2.f * (x * (v0.z + v2.x) + y * (v1.z + v2.y) - 2.f * z * (v0.x + v1.y) + w * (v0.y - v1.x));
+    return r;
+}
+
+// One thread per Gaussian; every output row is written (zeros when radii == 0).
+__global__ void __launch_bounds__(256)
+surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
+                      const float2* __restrict__ scales, const float4* __restrict__ rotations,
+                      const float* __restrict__ shs, const bool precomp, const ViewParams vc,
+                      const int Wb, const int Hb, const int* __restrict__ radii,
+                      const GeomRec* __restrict__ geom, const uint8_t* __restrict__ clamped,
+                      const float* __restrict__ gacc, float* __restrict__ dL_dmean2D,
+                      float* __restrict__ dL_dnormal, float* __restrict__ dL_dopacity,
+                      float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D,
+                      float* __restrict__ dL_dtransMat, float* __restrict__ dL_dsh,
+                      float* __restrict__ dL_dscale, float* __restrict__ dL_drot) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float4* ga = reinterpret_cast<const float4*>(gacc + (size_t)idx * GACC_STRIDE);
+    float4 a0 = ga[0], a1 = ga[1], a2 = ga[2], a3 = ga[3], a4 = ga[4];
+    float dT[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
+    float3 dcol = make_float3(a2.y, a2.z, a2.w);
+    float3 dnrm = make_float3(a3.x, a3.y, a3.z);
+    float dopa = a3.w;
+    float dm2x = a4.x, dm2y = a4.y;
+    float3 dmean = make_float3(0.f, 0.f, 0.f);
+    float2 dscale = make_float2(0.f, 0.f);
+    float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
+    float m2x = dm2x, m2y = dm2y;
+    float dTout[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) dTout[i] = dT[i];
+    const bool visible = radii[idx] > 0;
+    float view[16];
+    load16(vc.view, view);
+    if (dL_dsh != nullptr) {
+        float* o = dL_dsh + (size_t)idx * M * 3;
+        for (int j = 0; j < 3 * M; j++) o[j] = 0.f;
+    }
+    if (visible) {
+        GeomRec g = geom[idx];
+        float3 Tu, Tv, Tw, c0, c1, c2, normal = make_float3(0.f, 0.f, 0.f), p;
+        float Pm[3][4];
+        float2 sc = make_float2(0.f, 0.f);
+        float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (precomp) {
+            Tu = make_float3(g.tu.x, g.tu.y, g.tu.z);
+            Tv = make_float3(g.tv.x, g.tv.y, g.tv.z);
+            Tw = make_float3(g.tw.x, g.tw.y, g.tw.z);
+        } else {
+            // re-evaluated with scale_modifier ignored and Wb/Hb from float truncation
+            // (S/backward.cu:484-512,614-615)
+            p = make_float3(__ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1), __ldg(means3D + 3 * idx + 2));
+            q = __ldg(rotations + idx);
+            sc = __ldg(scales + idx);
+            quat_to_rot(q, c0, c1, c2);
+            float3 L0 = make_float3(c0.x * sc.x, c0.y * sc.x, c0.z * sc.x);
+            float3 L1 = make_float3(c1.x * sc.y, c1.y * sc.y, c1.z * sc.y);
+            // P = world2ndc * ndc2pix with the truncated Wb, Hb
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                float x = __ldg(vc.proj + 4 * r), y = __ldg(vc.proj + 4 * r + 1), w = __ldg(vc.proj + 4 * r + 3);
+                Pm[0][r] = x * ((float)Wb / 2.0f) + w * ((float)(Wb - 1) / 2.0f);
+                Pm[1][r] = y * ((float)Hb / 2.0f) + w * ((float)(Hb - 1) / 2.0f);
+                Pm[2][r] = w;
+            }
+            float t[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                t[i][0] = L0.x * Pm[i][0] + L0.y * Pm[i][1] + L0.z * Pm[i][2];
+                t[i][1] = L1.x * Pm[i][0] + L1.y * Pm[i][1] + L1.z * Pm[i][2];
+                t[i][2] = p.x * Pm[i][0] + p.y * Pm[i][1] + p.z * Pm[i][2] + Pm[i][3];
+            }
+            Tu = make_float3(t[0][0], t[0][1], t[0][2]);
+            Tv = make_float3(t[1][0], t[1][1], t[1][2]);
+            Tw = make_float3(t[2][0], t[2][1], t[2][2]);
+            normal = xformvec43(view, c2);
+        }
+        const bool aabb_branch = (dm2x != 0.f || dm2y != 0.f);
+        if (aabb_branch) {  // S/backward.cu:522-550
+            float3 tv3 = make_float3(9.0f, 9.0f, -1.0f);
+            float d = tv3.x * Tw.x * Tw.x + tv3.y * Tw.y * Tw.y + tv3.z * Tw.z * Tw.z;
+            float id = 1.0f / d;
+            float3 f = make_float3(tv3.x * id, tv3.y * id, tv3.z * id);
+            float3 dT0 = make_float3(dm2x * f.x * Tw.x, dm2x * f.y * Tw.y, dm2x * f.z * Tw.z);
+            float3 dT1 = make_float3(dm2y * f.x * Tw.x, dm2y * f.y * Tw.y, dm2y * f.z * Tw.z);
+            float3 dT3 = make_float3(dm2x * f.x * Tu.x + dm2y * f.x * Tv.x, dm2x * f.y * Tu.y + dm2y * f.y * Tv.y,
+                                     dm2x * f.z * Tu.z + dm2y * f.z * Tv.z);
+            float3 dLdf = make_float3(dm2x * Tu.x * Tw.x + dm2y * Tv.x * Tw.x, dm2x * Tu.y * Tw.y + dm2y * Tv.y * Tw.y,
+                                      dm2x * Tu.z * Tw.z + dm2y * Tv.z * Tw.z);
+            float dLdd = (dLdf.x * f.x + dLdf.y * f.y + dLdf.z * f.z) * (-1.0f / d);
+            dT3.x += dLdd * (tv3.x * Tw.x * 2.0f);
+            dT3.y += dLdd * (tv3.y * Tw.y * 2.0f);
+            dT3.z += dLdd * (tv3.z * Tw.z * 2.0f);
+            dT[0] += dT0.x; dT[1] += dT0.y; dT[2] += dT0.z;
+            dT[3] += dT1.x; dT[4] += dT1.y; dT[5] += dT1.z;
+            dT[6] += dT3.x; dT[7] += dT3.y; dT[8] += dT3.z;
+            if (precomp) {
+#pragma unroll
+                for (int i = 0; i < 9; i++) dTout[i] = dT[i];
+            }
+        }
+        if (!precomp) {
+            // dL_dM = P * transpose(dL_dT), S/backward.cu:555
+            float dM[3][3];
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+                    dM[j][r] = Pm[0][r] * dT[j] + Pm[1][r] * dT[3 + j] + Pm[2][r] * dT[6 + j];
+            float3 dtn = xformvec43T(view, dnrm);
+            float3 pv = xform43(view, p);
+            float cosv = -(pv.x * normal.x + pv.y * normal.y + pv.z * normal.z);
+            float mult = cosv > 0.f ? 1.f : -1.f;
+            dtn = make_float3(mult * dtn.x, mult * dtn.y, mult * dtn.z);
+            float3 dRS0 = make_float3(dM[0][0], dM[0][1], dM[0][2]);
+            float3 dRS1 = make_float3(dM[1][0], dM[1][1], dM[1][2]);
+            drot = quat_vjp(q, make_float3(dRS0.x * sc.x, dRS0.y * sc.x, dRS0.z * sc.x),
+                            make_float3(dRS1.x * sc.y, dRS1.y * sc.y, dRS1.z * sc.y), dtn);
+            dscale = make_float2(dot3(dRS0, c0), dot3(dRS1, c1));
+            dmean = make_float3(dM[2][0], dM[2][1], dM[2][2]);
+            if (shs != nullptr) {
+                float3 dm = sh_to_rgb_bwd(D, M, p, make_float3(__ldg(vc.campos), __ldg(vc.campos + 1), __ldg(vc.campos + 2)),
+                                          shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx, dcol,
+                                          dL_dsh + (size_t)idx * M * 3);
+                dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
+            }
+        } else if (shs != nullptr) {
+            // precomputed transMat with SH colours: S/backward.cu:630-631 still runs
+            p = make_float3(__ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1), __ldg(means3D + 3 * idx + 2));
+            float3 dm = sh_to_rgb_bwd(D, M, p, make_float3(__ldg(vc.campos), __ldg(vc.campos + 1), __ldg(vc.campos + 2)),
+                                      shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx, dcol,
+                                      dL_dsh + (size_t)idx * M * 3);
+            dmean = dm;
+        }
+        // densification hack, S/backward.cu:633-636: uses the stored dL_dtransMat and T[8]
+        float depth = g.tw.z;
+        m2x = dTout[2] * depth * 0.5f * (float)Wb;
+        m2y = dTout[5] * depth * 0.5f * (float)Hb;
+    }
+    dL_dmean2D[3 * (size_t)idx + 0] = m2x;
+    dL_dmean2D[3 * (size_t)idx + 1] = m2y;
+    dL_dmean2D[3 * (size_t)idx + 2] = 0.f;
+    dL_dnormal[3 * (size_t)idx + 0] = dnrm.x; dL_dnormal[3 * (size_t)idx + 1] = dnrm.y; dL_dnormal[3 * (size_t)idx + 2] = dnrm.z;
+    dL_dopacity[idx] = dopa;
+    dL_dcolor[3 * (size_t)idx + 0] = dcol.x; dL_dcolor[3 * (size_t)idx + 1] = dcol.y; dL_dcolor[3 * (size_t)idx + 2] = dcol.z;
+    dL_dmean3D[3 * (size_t)idx + 0] = dmean.x; dL_dmean3D[3 * (size_t)idx + 1] = dmean.y; dL_dmean3D[3 * (size_t)idx + 2] = dmean.z;
+#pragma unroll
+    for (int i = 0; i < 9; i++) dL_dtransMat[9 * (size_t)idx + i] = dTout[i];
+    if (dL_dscale) { dL_dscale[2 * (size_t)idx] = dscale.x; dL_dscale[2 * (size_t)idx + 1] = dscale.y; }
+    if (dL_drot) reinterpret_cast<float4*>(dL_drot)[idx] = drot;
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const ViewParams vc,
+                                    uint8_t* __restrict__ present) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    float3 p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    float view[16];
+    load16(vc.view, view);
+    present[idx] = xform43(view, p).z > 0.2f;
+}
+
+}  // namespace gsr

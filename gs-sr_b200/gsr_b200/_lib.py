@@ -1,0 +1,90 @@
+"""ctypes loader for libgsr_b200.so (C ABI in include/gsr_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_ROOT, "libgsr_b200.so")
+
+BUFFER_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+_fp = C.c_void_p  # device pointers travel as integers
+
+_LIB = None
+
+_ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "buffer callback failed",
+           -4: "prefiltered violation", -5: "num_rendered overflow"}
+
+
+def lib():
+    """Load libgsr_b200.so; fail loudly when it is absent (no fallback path exists)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libgsr_b200.so not found at {LIB_PATH}: build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C gs-sr_b200/csrc`. "
+            "gsr_b200 has no CPU/PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.gsr_last_error.restype = C.c_char_p
+    L.gsr_build_arch.restype = C.c_char_p
+    L.gsr_abi_version.restype = C.c_int
+    L.gsr_surfel_forward.restype = C.c_int
+    L.gsr_surfel_forward.argtypes = (
+        [BUFFER_FN, BUFFER_FN, BUFFER_FN, C.c_void_p, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int]
+        + [_fp] * 5 + [C.c_float] + [_fp] * 5 + [C.c_float, C.c_float, C.c_int] + [_fp] * 3 + [C.c_int, C.c_void_p])
+    L.gsr_surfel_backward.restype = C.c_int
+    L.gsr_surfel_backward.argtypes = (
+        [C.c_int] * 4 + [_fp, C.c_int, C.c_int] + [_fp] * 4 + [C.c_float] + [_fp] * 5 + [C.c_float, C.c_float]
+        + [_fp] * 15 + [C.c_int, C.c_void_p])
+    L.gsr_mark_visible.restype = C.c_int
+    L.gsr_mark_visible.argtypes = [C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]
+    _LIB = L
+    return L
+
+
+def check(rc, what):
+    if rc < 0:
+        msg = lib().gsr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed ({_ERRORS.get(rc, rc)}): {msg}")
+    return rc
+
+
+def ptr(t):
+    """Device pointer of a tensor, None (-> NULL) for empty / absent tensors, as the
+    reference glue turns empty tensors into nullptr."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+class TorchBuffers:
+    """The three resize callbacks of the reference protocol (S/rasterize_points.cu:31-37),
+    backed by torch's caching allocator on the tensors' device."""
+
+    def __init__(self, device):
+        import torch
+        self.device = device
+        self.tensors = {}
+        self._torch = torch
+
+        def make(name):
+            def cb(_user, nbytes):
+                try:
+                    t = self._torch.empty(int(nbytes) + 256, dtype=self._torch.uint8, device=self.device)
+                    self.tensors[name] = t
+                    return t.data_ptr()
+                except Exception:  # pragma: no cover - surfaced as GSR_E_ALLOC
+                    return 0
+            return BUFFER_FN(cb)
+
+        self.geom_fn = make("geom")
+        self.binning_fn = make("binning")
+        self.image_fn = make("image")
+
+    def get(self, name):
+        t = self.tensors.get(name)
+        if t is None:
+            t = self._torch.empty(0, dtype=self._torch.uint8, device=self.device)
+        return t

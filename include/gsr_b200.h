@@ -1,0 +1,103 @@
+/* gsr_b200.h -- C ABI of libgsr_b200.so, the B200 (sm_100a) rasterizer behind
+ * GS-SR's GaussianRasterizer / GaussianRasterizationSettings Python API.
+ *
+ * Every entry point replaces one function of the reference's native layer
+ * (cited per function; S/ = submodules/diff-surfel-rasterization, G/ =
+ * diff-gaussian-rasterization, L/ = diff-plane-rasterization, F/ =
+ * scaffold-filter, K/ = simple-knn under /root/reference).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *     float32 / int32, densely packed, row-major, exactly the layouts the
+ *     reference's torch glue passes down (S/rasterize_points.cu:108-132);
+ *   - a NULL pointer means "not provided", like the empty tensors the
+ *     reference wrapper turns into nullptr (S/diff_surfel_rasterization/__init__.py:198-208);
+ *   - `stream` is a cudaStream_t; all work is enqueued on it (the reference
+ *     uses the legacy default stream);
+ *   - the library never allocates device memory: scratch comes from the three
+ *     resize callbacks, the same protocol as the reference's
+ *     std::function<char*(size_t)> geometryBuffer/binningBuffer/imageBuffer
+ *     (S/cuda_rasterizer/rasterizer.h:31-34, S/rasterize_points.cu:31-37).
+ *     A callback must return a device pointer valid until the matching
+ *     backward call has been enqueued (>= 256-byte aligned), or NULL on failure;
+ *   - return value: >= 0 on success (forward: num_rendered), < 0 = GSR_E_*;
+ *     gsr_last_error() returns a thread-local message.  No C++ exception
+ *     crosses the boundary.
+ */
+#ifndef GSR_B200_H_
+#define GSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+
+enum {
+    GSR_OK = 0,
+    GSR_E_INVALID = -1,     /* bad argument (shape, NULL where required) */
+    GSR_E_CUDA = -2,        /* CUDA runtime error, see gsr_last_error() */
+    GSR_E_ALLOC = -3,       /* a resize callback returned NULL */
+    GSR_E_PREFILTERED = -4, /* prefiltered=1 but a point failed the near cull
+                               (the reference __trap()s, S/cuda_rasterizer/auxiliary.h:204-208) */
+    GSR_E_OVERFLOW = -5     /* num_rendered does not fit 32-bit indexing */
+};
+
+/* Resize callback: return a device buffer of at least `bytes` bytes. */
+typedef char* (*gsr_buffer_fn)(void* user, size_t bytes);
+
+int gsr_abi_version(void);
+const char* gsr_last_error(void);
+/* Name of the GPU architecture the library was compiled for ("sm_100a"). */
+const char* gsr_build_arch(void);
+
+/* ---- 2DGS surfel rasterizer: diff_surfel_rasterization ------------------ */
+
+/* Replaces CudaRasterizer::Rasterizer::forward
+ * (S/cuda_rasterizer/rasterizer.h:31-56, S/cuda_rasterizer/rasterizer_impl.cu:198-342)
+ * as called from RasterizeGaussiansCUDA (S/rasterize_points.cu:39-135).
+ *   out_color (3,H,W), out_others (11,H,W), radii (P) are fully written.
+ *   Exactly one of shs / colors_precomp and one of (scales+rotations) /
+ *   transMat_precomp must be non-NULL.  scales is (P,2) packed.
+ * Returns num_rendered. */
+int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer,
+                       gsr_buffer_fn imageBuffer, void* user,
+                       int P, int D, int M, const float* background, int width, int height,
+                       const float* means3D, const float* shs, const float* colors_precomp,
+                       const float* opacities, const float* scales, float scale_modifier,
+                       const float* rotations, const float* transMat_precomp,
+                       const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                       float tan_fovx, float tan_fovy, int prefiltered,
+                       float* out_color, float* out_others, int* radii, int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::backward
+ * (S/cuda_rasterizer/rasterizer.h:58-88, S/cuda_rasterizer/rasterizer_impl.cu:346-448)
+ * as called from RasterizeGaussiansBackwardCUDA (S/rasterize_points.cu:137-234).
+ * geom/binning/image buffers are the ones handed out during the forward call,
+ * R its return value.  All dL_* outputs are fully written (zeros where the
+ * reference leaves its torch::zeros untouched); dL_dnormal (P,3) is scratch the
+ * reference also exposes at this level.  dL_dsh may be NULL when M == 0. */
+int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                        const float* means3D, const float* shs, const float* colors_precomp,
+                        const float* scales, float scale_modifier, const float* rotations,
+                        const float* transMat_precomp, const float* viewmatrix,
+                        const float* projmatrix, const float* campos, float tan_fovx,
+                        float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+                        char* image_buffer, const float* dL_dpix, const float* dL_dothers,
+                        float* dL_dmean2D, float* dL_dnormal, float* dL_dopacity, float* dL_dcolor,
+                        float* dL_dmean3D, float* dL_dtransMat, float* dL_dsh, float* dL_dscale,
+                        float* dL_drot, int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible
+ * (S/cuda_rasterizer/rasterizer_impl.cu:141-153; identical in G/ and L/).
+ * present: P bytes (bool). */
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H_ */
