@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- rasterizer fwd+bwd Gaussians/s on the BASELINE workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json metric config, SURVEY.md section 8(d) cfg-B): one synthetic scene of
+2,000,000 surfels rendered at 1600x1060 with precomputed colours per rank (N ranks = N
+independent VastGaussian-style tiles with different seeds -> weak scaling, no data-path
+collective).  A "step" = GaussianRasterizer forward + autograd backward with fixed upstream
+gradients through the drop-in Python API (-> C ABI -> sm_100a kernels).
+
+One JSON line on rank 0:
+  value  : whole-job Gaussians/s, inputs resident in HBM (CUDA events, max over ranks)
+  e2e    : same metric with the step's inputs copied from pinned host memory and the rendered
+           colour image copied back inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+--impl reference times the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libref_surfel.so,
+compiled from /root/reference by oracle/build_ref.sh) on the same workload; when that library
+is absent it falls back to the CPU oracle port on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "gs-sr_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+P_DEFAULT, W_DEFAULT, H_DEFAULT = 2_000_000, 1600, 1060
+METRIC = "rasterizer fwd+bwd Gaussians/s @ 2M surfels x 1600x1060"
+PROF_NAMES = ["preprocess_fwd", "scan", "duplicate", "sort", "build_records", "render_fwd", "render_bwd",
+              "preprocess_bwd"]
+OWN_KERNELS_PER_STEP = 6  # preprocess_fwd, duplicate_with_keys, build_records, render_fwd, render_bwd, preprocess_bwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+    capture of the same workload (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[kernel]["dram_bytes"]
+    except Exception:
+        return None
+
+
+def algorithmic_bytes(P, V, R, N):
+    """SURVEY 8(d) per-unit figures restated for this repo's layouts (DESIGN.md 'Measurement')."""
+    return {
+        "preprocess_fwd": P * 40 + V * (64 + 16) + P * 8,
+        "render_fwd": R * 80 + N * 76,
+        "render_bwd": R * 80 + N * 76 + V * 80,
+        "whole_step": P * (40 + 24 + 112) + V * (64 + 12 + 76 + 148 + 44) + R * (12 + 24 * 6 + 8 + 80 + 80)
+        + N * (76 + 76),
+    }
+
+
+def build_inputs(P, W, H, seed, device):
+    import torch
+    import synth
+    sc = synth.make_scene(P, W, H, seed=seed)
+    gc, go = synth.make_upstream_grads(W, H, seed=seed + 1)
+    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(sc, k))).pin_memory()
+            for k in ("means3D", "scales", "rotations", "opacities", "colors")}
+    dev = {k: v.to(device) for k, v in host.items()}
+    cam = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in
+           dict(bg=sc.cam.bg, view=sc.cam.viewmatrix, proj=sc.cam.projmatrix, campos=sc.cam.campos).items()}
+    g = (torch.from_numpy(gc).to(device), torch.from_numpy(go).to(device))
+    return sc, host, dev, cam, g
+
+
+def run_ours(args, rank, world, device):
+    import torch
+    import gsr_b200
+    from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from gsr_b200 import shard
+    P, W, H = args.P, args.W, args.H
+    sc, host, dev, cam, (gct, got) = build_inputs(P, W, H, seed=rank * 17, device=device)
+    rs = GaussianRasterizationSettings(H, W, sc.cam.tanfovx, sc.cam.tanfovy, cam["bg"], 1.0, cam["view"], cam["proj"],
+                                       0, cam["campos"], False, False)
+    rast = GaussianRasterizer(rs)
+    state = {}
+
+    def step(inputs):
+        leaves = {k: v.detach().requires_grad_(True) for k, v in inputs.items()}
+        m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        color, radii, others = rast(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"],
+                                    colors_precomp=leaves["colors"], scales=leaves["scales"],
+                                    rotations=leaves["rotations"])
+        torch.autograd.backward([color, others], [gct, got])
+        state["radii"], state["color"], state["grad"] = radii, color, leaves["means3D"].grad
+        return color
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(dev)
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(dev)
+    e1.record()
+    barrier()
+    ms_resident = shard.max_over_ranks(e0.elapsed_time(e1), device)
+
+    # end-to-end: H2D of the step's inputs from pinned memory + D2H of the rendered image
+    out_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    staged = {k: torch.empty_like(v) for k, v in dev.items()}
+
+    def e2e_step():
+        for k in staged:
+            staged[k].copy_(host[k], non_blocking=True)
+        color = step(staged)
+        out_host.copy_(color.detach(), non_blocking=True)
+
+    for _ in range(min(2, args.warmup)):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = shard.max_over_ranks(e0.elapsed_time(e1), device)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    # per-kernel durations (cudaEvents inside the library, outside the timed regions)
+    L = gsr_b200.lib()
+    import ctypes
+    acc = np.zeros(16)
+    nprof = 3
+    for _ in range(nprof):
+        L.gsr_profile_enable(1)
+        step(dev)
+        buf = (ctypes.c_float * 16)()
+        L.gsr_profile_read(buf)
+        acc += np.array(list(buf))
+    L.gsr_profile_enable(0)
+    kernel_ms = {n: float(acc[i] / nprof) for i, n in enumerate(PROF_NAMES)}
+    V = int((state["radii"] > 0).sum().item())
+    return dict(ms_resident=ms_resident, ms_e2e=ms_e2e, clocks=clocks, h2d=h2d, d2h=d2h, kernel_ms=kernel_ms, V=V,
+                sc=sc, checksum=float(state["color"].double().sum().item()))
+
+
+def run_reference_cuda(args, rank, world, device):
+    import torch
+    from gsr_b200 import shard
+    from oracle.refcuda import RefSurfel
+    P, W, H = args.P, args.W, args.H
+    sc, host, dev, cam, (gct, got) = build_inputs(P, W, H, seed=rank * 17, device=device)
+    r = RefSurfel()
+    state = {}
+
+    def step(inp):
+        color, radii, others, R = r.forward(cam["bg"], cam["view"], cam["proj"], cam["campos"], W, H, sc.cam.tanfovx,
+                                            sc.cam.tanfovy, inp["means3D"], inp["opacities"], inp["scales"],
+                                            inp["rotations"], colors=inp["colors"])
+        r.backward(gct, got)
+        state["R"], state["radii"] = R, radii
+        return color
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(dev)
+    e1.record()
+    barrier()
+    ms_resident = shard.max_over_ranks(e0.elapsed_time(e1), device)
+    out_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    staged = {k: torch.empty_like(v) for k, v in dev.items()}
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        for k in staged:
+            staged[k].copy_(host[k], non_blocking=True)
+        color = step(staged)
+        out_host.copy_(color, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = shard.max_over_ranks(e0.elapsed_time(e1), device)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    return dict(ms_resident=ms_resident, ms_e2e=ms_e2e, h2d=h2d, d2h=out_host.numel() * 4, R=int(state["R"]),
+                V=int((state["radii"] > 0).sum().item()))
+
+
+def cpu_oracle_sample(P, W, H, stride=4):
+    """Bounded CPU sample: full preprocess + binning, render fwd+bwd on every `stride`-th tile in
+    x and y; throughput extrapolated as P / (t_bin + stride^2 * t_render)."""
+    import synth
+    from oracle.oracle import SurfelOracle
+    sc = synth.make_scene(P, W, H, seed=0)
+    gc, go = synth.make_upstream_grads(W, H, seed=1)
+    o = SurfelOracle()
+    t0 = time.perf_counter()
+    o.forward(sc.cam, sc.means3D, sc.opacities, sc.scales, sc.rotations, colors=sc.colors, tile_stride=1 << 20)
+    t_bin = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    f = o.forward(sc.cam, sc.means3D, sc.opacities, sc.scales, sc.rotations, colors=sc.colors, tile_stride=stride)
+    o.backward(gc, go, tile_stride=stride)
+    t_all = time.perf_counter() - t0
+    t_render = max(t_all - t_bin, 1e-9)
+    est = t_bin + stride * stride * t_render
+    return dict(value=P / est, cores=os.cpu_count(), t_bin=t_bin, t_render_sample=t_render,
+                sample=f"oracle/liborc.so (OpenMP, {os.cpu_count()} threads): full preprocess+binning of the "
+                       f"{P}-surfel scene ({t_bin:.1f}s) + render fwd+bwd on every {stride}th tile in x and y "
+                       f"({t_render:.1f}s); Gaussians/s = P / (t_bin + {stride * stride} * t_render)",
+                R=f["num_rendered"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--P", type=int, default=P_DEFAULT)
+    ap.add_argument("--W", type=int, default=W_DEFAULT)
+    ap.add_argument("--H", type=int, default=H_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=device)
+    workload = f"2DGS surfel rasterizer fwd+bwd, P={args.P} synthetic surfels (SURVEY 8(d) cfg-B), {args.W}x{args.H}, " \
+               "precomputed colours, one independent scene per rank"
+    base = {"metric": METRIC, "unit": "Gaussians/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "l2": "inputs + record stream (>850 MB/step) exceed the 126 MB L2; no flush",
+                       "parallelism": f"independent tiles x{world}, no data-path collective"}}
+
+    if args.impl == "reference":
+        from oracle import refcuda
+        if refcuda.available("surfel"):
+            r = run_reference_cuda(args, rank, world, device)
+            if rank == 0:
+                v = args.P * world * args.steps / (r["ms_resident"] * 1e-3)
+                ve = args.P * world * args.steps / (r["ms_e2e"] * 1e-3)
+                base.update({"impl": "reference", "value": v, "ms_per_step": r["ms_resident"] / args.steps,
+                             "e2e": {"value": ve, "unit": "Gaussians/s", "h2d_bytes_per_step": r["h2d"],
+                                     "d2h_bytes_per_step": r["d2h"]},
+                             "cpu_baseline": {"value": v, "unit": "Gaussians/s", "cores": 0, "kind": "reference",
+                                              "sample": "the reference has no CPU path: its own UNMODIFIED CUDA "
+                                                        "kernels (diff-surfel-rasterization compiled for sm_100a "
+                                                        "by oracle/build_ref.sh) on the full workload on the GPU"},
+                             "stats": {"num_rendered": r["R"], "visible": r["V"]}, "gpu_launches": 0})
+                print(json.dumps(base))
+        else:
+            if rank == 0:
+                c = cpu_oracle_sample(args.P, args.W, args.H)
+                base.update({"impl": "reference", "value": c["value"], "ms_per_step": args.P / c["value"] * 1e3,
+                             "n_gpus": 1, "e2e": {"value": c["value"], "unit": "Gaussians/s", "h2d_bytes_per_step": 0,
+                                                  "d2h_bytes_per_step": 0},
+                             "cpu_baseline": {"value": c["value"], "unit": "Gaussians/s", "cores": c["cores"],
+                                              "kind": "port", "sample": c["sample"]}, "gpu_launches": 0})
+                print(json.dumps(base))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    r = run_ours(args, rank, world, device)
+    if rank == 0:
+        v = args.P * world * args.steps / (r["ms_resident"] * 1e-3)
+        ve = args.P * world * args.steps / (r["ms_e2e"] * 1e-3)
+        peak, peak_src = measured_peak()
+        N = args.W * args.H
+        # R is read back from the oracle-free path: num_rendered of rank 0's scene
+        from diff_surfel_rasterization import last_num_rendered
+        R = last_num_rendered()
+        ab = algorithmic_bytes(args.P, r["V"], R, N)
+        dom = max(("render_fwd", "render_bwd"), key=lambda k: r["kernel_ms"][k])
+        achieved = ab[dom] / (r["kernel_ms"][dom] * 1e-3) / 1e9
+        base.update({
+            "value": v, "ms_per_step": r["ms_resident"] / args.steps,
+            "e2e": {"value": ve, "unit": "Gaussians/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "gpu_launches": OWN_KERNELS_PER_STEP * args.steps,
+            "clocks": r["clocks"],
+            "roofline": {"bound": "hbm", "kernel": f"gsr::surfel_{dom}", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                         "algorithmic_bytes": ab[dom], "kernel_ms": r["kernel_ms"][dom],
+                         "whole_step_frac": ab["whole_step"] / (r["ms_resident"] / args.steps * 1e-3) / 1e9 / peak},
+            "kernel_ms": r["kernel_ms"],
+            "stats": {"num_rendered": R, "visible": r["V"], "pixels": N, "checksum": r["checksum"]},
+        })
+        if world == 1 and not args.no_cpu_baseline:
+            c = cpu_oracle_sample(args.P, args.W, args.H)
+            base["cpu_baseline"] = {"value": c["value"], "unit": "Gaussians/s", "cores": c["cores"], "kind": "port",
+                                    "sample": c["sample"]}
+        print(json.dumps(base))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -98,10 +98,24 @@ static ViewParams make_view(const float* view, const float* proj, const float* c
     return vc;
 }
 
-static bool no_cull_env() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("GSR_NO_CULL"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
+// ---- runtime options (debug / measurement only; defaults are the product path) ----
+static int g_no_cull = -1;   // 1: contribution boxes disabled (every pair evaluated, as the reference does)
+static bool no_cull() {
+    if (g_no_cull < 0) { const char* e = getenv("GSR_NO_CULL"); g_no_cull = (e && e[0] == '1') ? 1 : 0; }
+    return g_no_cull == 1;
+}
+
+// ---- per-kernel device timing (cudaEvents on the caller's stream, off by default) ----
+// bench.py needs the dominant kernel's duration measured live, outside any profiler.
+struct Prof {
+    bool on = false, created = false;
+    cudaEvent_t ev[GSR_PROF_SLOTS][2];
+    bool used[GSR_PROF_SLOTS];
+};
+static Prof g_prof;
+static inline void prof_begin(int slot, cudaStream_t s) { if (g_prof.on) cudaEventRecord(g_prof.ev[slot][0], s); }
+static inline void prof_end(int slot, cudaStream_t s) {
+    if (g_prof.on) { cudaEventRecord(g_prof.ev[slot][1], s); g_prof.used[slot] = true; }
 }
 
 }  // namespace gsr
@@ -113,6 +127,35 @@ extern "C" {
 int gsr_abi_version(void) { return GSR_ABI_VERSION; }
 const char* gsr_last_error(void) { return g_err; }
 const char* gsr_build_arch(void) { return "sm_100a"; }
+
+int gsr_set_option(const char* name, int value) {
+    if (!name) return GSR_E_INVALID;
+    if (!strcmp(name, "no_cull")) { g_no_cull = value ? 1 : 0; return GSR_OK; }
+    set_error("gsr_set_option: unknown option %s", name);
+    return GSR_E_INVALID;
+}
+
+int gsr_profile_enable(int on) {
+    if (on && !g_prof.created) {
+        for (int i = 0; i < GSR_PROF_SLOTS; i++)
+            for (int j = 0; j < 2; j++) GSR_CUDA_CHECK(cudaEventCreate(&g_prof.ev[i][j]));
+        g_prof.created = true;
+    }
+    for (int i = 0; i < GSR_PROF_SLOTS; i++) g_prof.used[i] = false;
+    g_prof.on = on != 0;
+    return GSR_OK;
+}
+
+int gsr_profile_read(float* ms_host) {
+    if (!ms_host || !g_prof.created) { set_error("gsr_profile_read: profiling was never enabled"); return GSR_E_INVALID; }
+    for (int i = 0; i < GSR_PROF_SLOTS; i++) {
+        ms_host[i] = -1.0f;
+        if (!g_prof.used[i]) continue;
+        GSR_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[i][1]));
+        GSR_CUDA_CHECK(cudaEventElapsedTime(&ms_host[i], g_prof.ev[i][0], g_prof.ev[i][1]));
+    }
+    return GSR_OK;
+}
 
 int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer, gsr_buffer_fn imageBuffer,
                        void* user, int P, int D, int M, const float* background, int width, int height,
@@ -155,12 +198,16 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         GeomWs::carve(gw, align256(gbase), P, scan_bytes);
         GSR_CUDA_CHECK(cudaMemsetAsync(gw.flags, 0, 32 * sizeof(int), s));
 
+        prof_begin(GSR_PROF_PREPROCESS_FWD, s);
         surfel_preprocess_fwd<<<(P + 255) / 256, 256, 0, s>>>(
             P, D, M, means3D, (const float2*)scales, (const float4*)rotations, opacities, shs, transMat_precomp,
-            colors_precomp != nullptr, vc, prefiltered != 0, no_cull_env(), radii, gw.geom, gw.cbox, gw.tiles,
+            colors_precomp != nullptr, vc, prefiltered != 0, no_cull(), radii, gw.geom, gw.cbox, gw.tiles,
             gw.rgb, gw.clamped, gw.flags);
+        prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
+        prof_begin(GSR_PROF_SCAN, s);
         GSR_CUDA_CHECK(inclusive_scan(gw.scan_tmp, gw.scan_tmp_bytes, gw.tiles, gw.offsets, P, s));
+        prof_end(GSR_PROF_SCAN, s);
         // num_rendered sizes the binning buffer: same single read-back as the reference
         // (S/rasterizer_impl.cu:282), plus the prefiltered flag.
         uint32_t Ru = 0;
@@ -180,19 +227,27 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     BinWs::carve(bw, align256(bbase), R, P, sort_bytes);
 
     if (R > 0) {
+        prof_begin(GSR_PROF_DUPLICATE, s);
         duplicate_with_keys<<<(P + 255) / 256, 256, 0, s>>>(P, gw.geom, radii, gw.offsets, vc.gx, vc.gy,
                                                             bw.keys_unsorted, bw.vals_unsorted);
+        prof_end(GSR_PROF_DUPLICATE, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         int end_bit = 32 + (int)ceil_log2_tiles((uint32_t)ntiles);
+        prof_begin(GSR_PROF_SORT, s);
         GSR_CUDA_CHECK(sort_pairs(bw.sort_tmp, bw.sort_tmp_bytes, bw.keys_unsorted, bw.keys, bw.vals_unsorted,
                                   bw.vals, R, end_bit, s));
+        prof_end(GSR_PROF_SORT, s);
         const float* colors = colors_precomp ? colors_precomp : gw.rgb;
+        prof_begin(GSR_PROF_BUILD_RECORDS, s);
         build_records<<<(R + 255) / 256, 256, 0, s>>>(R, bw.keys, bw.vals, gw.geom, gw.cbox, colors, vc.gx,
                                                       bw.recs, iw.ranges);
+        prof_end(GSR_PROF_BUILD_RECORDS, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }
+    prof_begin(GSR_PROF_RENDER_FWD, s);
     surfel_render_fwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.recs, W, H, vc.gx, background,
                                                   iw.final_T, iw.n_contrib, out_color, out_others);
+    prof_end(GSR_PROF_RENDER_FWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
     (void)N;
     if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -229,16 +284,20 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
 
     GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * GACC_STRIDE * sizeof(float), s));
     if (R > 0) {
+        prof_begin(GSR_PROF_RENDER_BWD, s);
         surfel_render_bwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.recs, W, H, vc.gx, background,
                                                       iw.final_T, iw.n_contrib, dL_dpix, dL_dothers,
                                                       bw.gacc);
+        prof_end(GSR_PROF_RENDER_BWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }
     const bool precomp = (scales == nullptr);
+    prof_begin(GSR_PROF_PREPROCESS_BWD, s);
     surfel_preprocess_bwd<<<(P + 255) / 256, 256, 0, s>>>(
         P, D, M, means3D, (const float2*)scales, (const float4*)rotations, shs, precomp, vc, Wb, Hb, radii,
         gw.geom, gw.clamped, bw.gacc, dL_dmean2D, dL_dnormal, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat,
         shs ? dL_dsh : nullptr, dL_dscale, dL_drot);
+    prof_end(GSR_PROF_PREPROCESS_BWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
     if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return GSR_OK;

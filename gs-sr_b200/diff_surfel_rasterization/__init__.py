@@ -56,6 +56,14 @@ def _f32c(t, name, device):
     return t.contiguous()
 
 
+_LAST = {"num_rendered": 0}
+
+
+def last_num_rendered():
+    """num_rendered (R) of the most recent forward call in this process (bench statistics)."""
+    return _LAST["num_rendered"]
+
+
 def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -105,6 +113,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)), ptr(color), ptr(others),
                     ptr(radii), int(bool(rs.debug)), _stream_ptr(dev)), "gsr_surfel_forward")
 
+        _LAST["num_rendered"] = num_rendered
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.dims = (P, M, H, W)

@@ -54,6 +54,32 @@ const char* gsr_last_error(void);
 /* Name of the GPU architecture the library was compiled for ("sm_100a"). */
 const char* gsr_build_arch(void);
 
+/* ---- measurement / debug hooks (no reference counterpart) ------------------ */
+
+/* Per-kernel device timing with cudaEvents recorded on the caller's stream around
+ * each launch of the next forward/backward calls (bench.py's roofline numbers).
+ * gsr_profile_read() fills GSR_PROF_SLOTS floats (milliseconds, -1 = not run) for the
+ * most recent call of each kernel; it blocks on the recorded events.
+ * Not thread-safe; off by default. */
+enum {
+    GSR_PROF_PREPROCESS_FWD = 0,
+    GSR_PROF_SCAN = 1,
+    GSR_PROF_DUPLICATE = 2,
+    GSR_PROF_SORT = 3,
+    GSR_PROF_BUILD_RECORDS = 4,
+    GSR_PROF_RENDER_FWD = 5,
+    GSR_PROF_RENDER_BWD = 6,
+    GSR_PROF_PREPROCESS_BWD = 7,
+    GSR_PROF_SLOTS = 16
+};
+int gsr_profile_enable(int on);
+int gsr_profile_read(float* ms_host);
+
+/* Runtime switches for validation.  "no_cull" = 1 disables the conservative
+ * contribution boxes so every (pixel, splat) pair of a tile is evaluated like the
+ * reference does; results must not change (tests/test_surfel_gpu.py). */
+int gsr_set_option(const char* name, int value);
+
 /* ---- 2DGS surfel rasterizer: diff_surfel_rasterization ------------------ */
 
 /* Replaces CudaRasterizer::Rasterizer::forward

@@ -32,7 +32,8 @@ def _lib(double=False):
         lib.orc_surfel_forward.restype = C.c_void_p
         lib.orc_surfel_num_rendered.restype = C.c_int64
         lib.orc_surfel_k_eval.restype = C.c_int64
-        for fn in ("orc_surfel_num_rendered", "orc_surfel_k_eval", "orc_surfel_free"):
+        lib.orc_surfel_k_blend.restype = C.c_int64
+        for fn in ("orc_surfel_num_rendered", "orc_surfel_k_eval", "orc_surfel_k_blend", "orc_surfel_free"):
             getattr(lib, fn).argtypes = [C.c_void_p]
         _LIBS[name] = lib
     return _LIBS[name]
@@ -95,7 +96,8 @@ class SurfelOracle:
             raise RuntimeError("prefiltered trap: a point was culled although prefiltered is set")
         return dict(color=color, others=others, radii=radii,
                     num_rendered=int(self.lib.orc_surfel_num_rendered(C.c_void_p(h))),
-                    k_eval=int(self.lib.orc_surfel_k_eval(C.c_void_p(h))))
+                    k_eval=int(self.lib.orc_surfel_k_eval(C.c_void_p(h))),
+                    k_blend=int(self.lib.orc_surfel_k_blend(C.c_void_p(h))))
 
     def geom(self):
         P = self.P

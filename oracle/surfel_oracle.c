@@ -84,6 +84,7 @@ typedef struct {
     real* final_T;       /* 3N: T, M1, M2 */
     uint32_t* n_contrib; /* 2N: last contributor, median contributor */
     int64_t k_eval;      /* (pixel,splat) pairs walked in forward (bench statistic) */
+    int64_t k_blend;     /* pairs that passed every test and were blended */
 } OrcSurfel;
 
 /* S/aux:81-110 */
@@ -401,9 +402,9 @@ OrcSurfel* orc_surfel_forward(int P, int D, int M, const float* bg, int W, int H
     /* ---- render, S/fwd:256-448 ---- */
     const real* feat = colors ? colors : o->rgb;
     const real* TM = Tpre ? Tpre : o->transMat;
-    int64_t k_eval = 0;
+    int64_t k_eval = 0, k_blend = 0;
     if (tile_stride < 1) tile_stride = 1;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : k_eval)
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : k_eval, k_blend)
     for (int tile = 0; tile < ntiles; tile++) {
         int tx = tile % o->gx, ty = tile / o->gx;
         if (tx % tile_stride || ty % tile_stride) continue;
@@ -455,6 +456,7 @@ OrcSurfel* orc_surfel_forward(int P, int D, int M, const float* bg, int W, int H
                     for (int c = 0; c < 3; c++) C[c] += feat[3 * g + c] * w;
                     T = test_T;
                     last_contributor = contributor;
+                    k_blend++;
                 }
                 k_eval += contributor;
                 o->final_T[pix_id] = T;
@@ -476,6 +478,7 @@ OrcSurfel* orc_surfel_forward(int P, int D, int M, const float* bg, int W, int H
             }
     }
     o->k_eval = k_eval;
+    o->k_blend = k_blend;
     free(means); free(shs); free(colors); free(opac); free(scales); free(rots); free(Tpre);
     return o;
 }
@@ -483,6 +486,7 @@ OrcSurfel* orc_surfel_forward(int P, int D, int M, const float* bg, int W, int H
 /* accessors for tests */
 int64_t orc_surfel_num_rendered(OrcSurfel* o) { return o->R; }
 int64_t orc_surfel_k_eval(OrcSurfel* o) { return o->k_eval; }
+int64_t orc_surfel_k_blend(OrcSurfel* o) { return o->k_blend; }
 void orc_surfel_get_geom(OrcSurfel* o, float* depths, float* xy, float* transMat, float* normal_opacity,
                          float* rgb, int* tiles_touched) {
     for (int i = 0; i < o->P; i++) {

@@ -41,6 +41,13 @@ def parity(P, W, H, sh, seed, oracle=True):
         if hz_ref_available():
             res["ref_fwd_vs_orc"] = hz.compare_forward(ref, orc, ("refcuda", "oracle"))
             res["ref_grad_vs_orc"] = hz.compare_grads(ref["grads"], orc["grads"], ("refcuda", "oracle"))
+            if os.environ.get("GSR_DUMP"):
+                np.savez_compressed(f"gpurun_out/dump_P{P}_sh{int(sh)}.npz",
+                                    **{f"ref_{k}": v for k, v in ref["grads"].items()},
+                                    **{f"orc_{k}": v for k, v in orc["grads"].items()},
+                                    **{f"mine_{k}": v for k, v in mine["grads"].items() if v is not None},
+                                    ref_color=ref["color"], ref_others=ref["others"], mine_color=mine["color"],
+                                    mine_others=mine["others"], ref_radii=ref["radii"], mine_radii=mine["radii"])
     return res
 
 

@@ -1,0 +1,117 @@
+"""CPU tests: the oracle (oracle/surfel_oracle.c) against the golden vectors captured
+from the UNMODIFIED reference CUDA kernels on a B200 (tests/golden/make_golden.py).
+
+Tolerances (north_star: forward <= 1e-4 rel L-inf, gradients <= 1e-3 rel):
+  * forward images: rel L-inf (relative to the channel's max) <= 1e-4 after excluding the
+    1e-3 fraction of pixels with the largest deviation.  Two correct float32 rasterizers
+    disagree on single pixels when a splat's alpha lands within an ulp of 1/255 or T within
+    an ulp of 1e-4 / 0.5 (each flip moves one pixel by up to ~1e-2); the raw value is
+    bounded loosely (<= 2e-2) to catch real errors.
+  * the distortion channel (allmap[6]) is formed as m^2*A + M2 - 2*m*M1 with heavy float32
+    cancellation: the reference CUDA output itself deviates from a float64 evaluation by
+    1e-4 .. 6e-4 (measured per case), so that channel is held to 2e-3.
+  * gradients: rel L-inf (relative to the tensor's max) <= 1e-3 after excluding the 2e-3
+    fraction of Gaussians with the largest deviation, and rel L2 <= 5e-3 overall: edge-on
+    surfels have ill-conditioned float32 gradients (the reference itself deviates from a
+    float64 evaluation by 2e-3 on such splats, see DESIGN.md "Parity").
+"""
+import os
+
+import numpy as np
+import pytest
+
+import harness as hz
+from golden.cases import CASES, build_case
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FWD_TOL, FWD_RAW_TOL, DIST_TOL = 1e-4, 2e-2, 2e-3
+GRAD_TOL, GRAD_L2_TOL = 1e-3, 5e-3
+
+
+def load(name):
+    path = os.path.join(GOLD, f"surfel_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"golden fixture {path} missing")
+    return np.load(path)
+
+
+def robust_grad_err(a, b, frac=2e-3):
+    a = np.asarray(a, np.float64).reshape(a.shape[0], -1)
+    b = np.asarray(b, np.float64).reshape(b.shape[0], -1)
+    d = np.abs(a - b).max(axis=1)
+    k = int(np.ceil(frac * d.size))
+    if 0 < k < d.size:
+        d = np.partition(d, d.size - k - 1)[: d.size - k]
+    return d.max() / max(np.abs(b).max(), 1e-30)
+
+
+def check_forward(out, gold):
+    assert int(out["num_rendered"]) == int(gold["num_rendered"])
+    assert (out["radii"] != gold["radii"]).sum() <= max(1, out["radii"].size // 2000)
+    for name, a, b in [("color", out["color"], gold["color"])] + [
+            (f"others[{c}]", out["others"][c], gold["others"][c]) for c in range(7)]:
+        tol = DIST_TOL if name == "others[6]" else FWD_TOL
+        assert hz.rel_linf(a, b, 1e-3) <= tol, name
+        assert hz.rel_linf(a, b) <= FWD_RAW_TOL, name
+    # surf idx (channel 7) and median normal (8..10): identical except on flipped pixels
+    assert (out["others"][7] != gold["others"][7]).mean() <= 2e-3
+    for c in (8, 9, 10):
+        assert hz.rel_linf(out["others"][c], gold["others"][c], 2e-3) <= FWD_TOL
+
+
+def check_grads(grads, gold, keys):
+    for k in keys:
+        g = gold["grad_" + k]
+        if g.size == 0:
+            continue
+        a = np.asarray(grads[k]).reshape(g.shape)
+        assert robust_grad_err(a, g) <= GRAD_TOL, k
+        l2 = np.linalg.norm(a.astype(np.float64) - g) / max(np.linalg.norm(g), 1e-30)
+        assert l2 <= GRAD_L2_TOL, (k, l2)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_cuda(name):
+    gold = load(name)
+    sc, gc, go, kw = build_case(name)
+    out = hz.run_oracle_surfel(sc, gc, go, **kw)
+    check_forward(out, gold)
+    keys = ["means2D", "colors", "opacities", "means3D", "transMat", "shs"]
+    if "transMat_precomp" not in kw:
+        keys += ["scales", "rotations"]
+    check_grads(out["grads"], gold, keys)
+
+
+def test_oracle_double_build_agrees():
+    sc, gc, go, kw = build_case("colors")
+    a = hz.run_oracle_surfel(sc, gc, go, **kw)
+    b = hz.run_oracle_surfel(sc, gc, go, double=True, **kw)
+    assert hz.rel_linf(a["color"], b["color"], 1e-3) <= 1e-4
+    for k in ("colors", "opacities", "scales"):
+        assert robust_grad_err(a["grads"][k], b["grads"][k]) <= 1e-3
+
+
+def test_oracle_empty_and_all_culled():
+    import synth
+    sc = synth.make_scene(50, 48, 32, seed=3)
+    sc.means3D[:, 2] = -1.0  # everything behind the camera
+    out = hz.run_oracle_surfel(sc, *synth.make_upstream_grads(48, 32))
+    assert out["num_rendered"] == 0 and (out["radii"] == 0).all()
+    assert np.allclose(out["color"], sc.cam.bg[:, None, None])
+    assert all(np.abs(v).max() == 0 for v in out["grads"].values() if v.size)
+
+
+def test_oracle_binning_is_sorted_and_stable():
+    sc, gc, go, kw = build_case("colors")
+    out = hz.run_oracle_surfel(sc)
+    o = out["oracle"]
+    pl, rg = o.binning()
+    depth = o.geom()["depths"]
+    for t in range(rg.shape[0]):
+        a, b = int(rg[t, 0]), int(rg[t, 1])
+        ids = pl[a:b].astype(np.int64)
+        d = depth[ids]
+        assert (np.diff(d) >= 0).all()
+        ties = np.diff(d) == 0
+        assert (np.diff(ids)[ties] > 0).all()
+    assert int(rg[:, 1].max()) == out["num_rendered"]

@@ -1,0 +1,198 @@
+"""GPU parity tests (pytest -m gpu): the product path (drop-in Python API -> C ABI ->
+hand-written sm_100a kernels) against
+  * the golden vectors captured from the unmodified reference CUDA kernels,
+  * the CPU oracle on seeded scenes (sizes the oracle finishes in seconds),
+  * the reference CUDA build itself when oracle/_ref/libref_surfel.so travelled with the repo,
+  * size-independent identities at the BASELINE size (2M surfels, 1600x1060).
+Tolerances are the ones derived in tests/test_oracle_golden.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import harness as hz
+import synth
+from golden.cases import CASES, build_case
+from test_oracle_golden import (DIST_TOL, FWD_RAW_TOL, FWD_TOL, GRAD_L2_TOL, GRAD_TOL, load,
+                                robust_grad_err)
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_forward_close(a, b, radii_slack=2000):
+    assert (a["radii"] != b["radii"]).sum() <= max(1, a["radii"].size // radii_slack)
+    pairs = [("color", a["color"], b["color"])] + [(f"others[{c}]", a["others"][c], b["others"][c]) for c in range(7)]
+    for name, x, y in pairs:
+        tol = DIST_TOL if name == "others[6]" else FWD_TOL
+        assert hz.rel_linf(x, y, 1e-3) <= tol, (name, hz.rel_linf(x, y, 1e-3))
+        assert hz.rel_linf(x, y) <= FWD_RAW_TOL, (name, hz.rel_linf(x, y))
+    assert (a["others"][7] != b["others"][7]).mean() <= 2e-3
+
+
+def assert_grads_close(ga, gb, keys):
+    for k in keys:
+        y = np.asarray(gb[k])
+        if y.size == 0 or ga.get(k) is None:
+            continue
+        x = np.asarray(ga[k]).reshape(y.shape)
+        assert robust_grad_err(x, y) <= GRAD_TOL, (k, robust_grad_err(x, y))
+        l2 = np.linalg.norm(x.astype(np.float64) - y) / max(np.linalg.norm(y), 1e-30)
+        assert l2 <= GRAD_L2_TOL, (k, l2)
+
+
+def grad_keys(kw, sc):
+    keys = ["means2D", "opacities", "means3D"]
+    keys += ["shs"] if sc.shs is not None else ["colors"]
+    keys += ["transMat"] if "transMat_precomp" in kw else ["scales", "rotations"]
+    return keys
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_product_matches_golden_reference_vectors(name):
+    gold = load(name)
+    sc, gc, go, kw = build_case(name)
+    out = hz.run_product_surfel(sc, gc, go, **kw)
+    g = dict(color=gold["color"], others=gold["others"], radii=gold["radii"])
+    assert_forward_close(out, g)
+    gg = {k[5:]: gold[k] for k in gold.files if k.startswith("grad_")}
+    assert_grads_close(out["grads"], gg, grad_keys(kw, sc))
+
+
+@pytest.mark.parametrize("P,W,H,sh,seed", [(20000, 320, 240, False, 11), (5000, 320, 240, True, 12),
+                                           (30000, 333, 177, False, 13)])
+def test_product_matches_oracle(P, W, H, sh, seed):
+    sc = synth.make_scene(P, W, H, seed=seed, sh=sh, rotate_camera=True, bg=(0.1, 0.2, 0.3))
+    gc, go = synth.make_upstream_grads(W, H, seed=seed + 1)
+    out = hz.run_product_surfel(sc, gc, go)
+    orc = hz.run_oracle_surfel(sc, gc, go)
+    assert_forward_close(out, orc)
+    assert_grads_close(out["grads"], orc["grads"], grad_keys({}, sc))
+
+
+def test_product_matches_reference_cuda_build():
+    from oracle import refcuda
+    if not refcuda.available("surfel"):
+        pytest.skip("oracle/_ref/libref_surfel.so not present")
+    sc = synth.make_scene(100000, 800, 800, seed=21, sh=True)
+    gc, go = synth.make_upstream_grads(800, 800, seed=22)
+    tt = hz.to_torch(sc)
+    out = hz.run_product_surfel(sc, gc, go, tt=tt)
+    ref = hz.run_refcuda_surfel(sc, gc, go, tt=tt)
+    assert_forward_close(out, ref)
+    assert_grads_close(out["grads"], ref["grads"], grad_keys({}, sc))
+
+
+def test_culling_never_changes_results():
+    """The conservative contribution boxes only skip pairs whose alpha < 1/255."""
+    import gsr_b200
+    sc = synth.make_scene(40000, 400, 300, seed=31, rotate_camera=True, sigma_px=4.0)
+    gc, go = synth.make_upstream_grads(400, 300, seed=32)
+    L = gsr_b200.lib()
+    try:
+        L.gsr_set_option(b"no_cull", 1)
+        full = hz.run_product_surfel(sc, gc, go)
+    finally:
+        L.gsr_set_option(b"no_cull", 0)
+    cul = hz.run_product_surfel(sc, gc, go)
+    # forward is bit-identical: same pairs blended in the same order
+    assert np.array_equal(full["color"], cul["color"])
+    assert np.array_equal(full["others"], cul["others"])
+    for k in ("means3D", "colors", "opacities", "scales", "rotations", "means2D"):
+        assert hz.rel_linf(cul["grads"][k], full["grads"][k]) <= 2e-5, k  # atomic order only
+
+
+def test_empty_all_culled_and_background():
+    sc = synth.make_scene(64, 48, 32, seed=3, bg=(0.25, 0.5, 0.75))
+    gc, go = synth.make_upstream_grads(48, 32)
+    sc.means3D[:, 2] = -1.0
+    out = hz.run_product_surfel(sc, gc, go)
+    assert (out["radii"] == 0).all()
+    assert np.allclose(out["color"], sc.cam.bg[:, None, None])
+    assert np.abs(out["others"][:7]).max() == 0 and (out["others"][7] == -1).all()
+    for k, v in out["grads"].items():
+        assert v is None or np.abs(v).max() == 0, k
+    # P == 0: zero-filled outputs without a launch (S/rasterize_points.cu:99-100)
+    from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    tt = hz.to_torch(sc)
+    rs = GaussianRasterizationSettings(32, 48, sc.cam.tanfovx, sc.cam.tanfovy, tt["bg"], 1.0, tt["view"],
+                                       tt["proj"], 0, tt["campos"], False, False)
+    e = torch.zeros((0, 3), device="cuda")
+    color, radii, others = GaussianRasterizer(rs)(means3D=e, means2D=e, opacities=torch.zeros((0, 1), device="cuda"),
+                                                   colors_precomp=e, scales=torch.zeros((0, 2), device="cuda"),
+                                                   rotations=torch.zeros((0, 4), device="cuda"))
+    assert color.shape == (3, 32, 48) and float(color.abs().max()) == 0 and radii.numel() == 0
+
+
+def test_mark_visible_and_prefiltered_error():
+    from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from oracle.oracle import mark_visible
+    sc = synth.make_scene(5000, 64, 48, seed=5, rotate_camera=True, behind_fraction=0.3)
+    tt = hz.to_torch(sc)
+    mk = lambda pre: GaussianRasterizationSettings(48, 64, sc.cam.tanfovx, sc.cam.tanfovy, tt["bg"], 1.0,  # noqa: E731
+                                                   tt["view"], tt["proj"], 0, tt["campos"], pre, False)
+    vis = GaussianRasterizer(mk(False)).markVisible(tt["means3D"]).cpu().numpy()
+    assert np.array_equal(vis, mark_visible(sc.means3D, sc.cam.viewmatrix))
+    m2 = torch.zeros_like(tt["means3D"])
+    with pytest.raises(RuntimeError, match="prefiltered"):
+        GaussianRasterizer(mk(True))(means3D=tt["means3D"], means2D=m2, opacities=tt["opacities"],
+                                     colors_precomp=tt["colors"], scales=tt["scales"], rotations=tt["rotations"])
+
+
+def test_strided_scales_view_is_honoured():
+    """GS-SR passes scaling[:, :2] (stride 3) for scaffold/octree-2DGS (scaffold_2dgs_scene.py:17)."""
+    from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    sc = synth.make_scene(3000, 96, 64, seed=41, sigma_px=3.0)
+    gc, go = synth.make_upstream_grads(96, 64, seed=42)
+    base = hz.run_product_surfel(sc, gc, go)
+    tt = hz.to_torch(sc)
+    s3 = torch.cat([tt["scales"], torch.ones_like(tt["scales"][:, :1])], dim=1).requires_grad_(True)
+    rs = GaussianRasterizationSettings(64, 96, sc.cam.tanfovx, sc.cam.tanfovy, tt["bg"], 1.0, tt["view"],
+                                       tt["proj"], 0, tt["campos"], False, False)
+    m2 = torch.zeros_like(tt["means3D"], requires_grad=True)
+    color, radii, others = GaussianRasterizer(rs)(means3D=tt["means3D"], means2D=m2, opacities=tt["opacities"],
+                                                   colors_precomp=tt["colors"], scales=s3[:, :2],
+                                                   rotations=tt["rotations"])
+    torch.autograd.backward([color, others], [torch.from_numpy(gc).cuda(), torch.from_numpy(go).cuda()])
+    assert np.array_equal(color.detach().cpu().numpy(), base["color"])
+    g = s3.grad.cpu().numpy()
+    assert hz.rel_linf(g[:, :2], base["grads"]["scales"]) <= 2e-5 and np.abs(g[:, 2]).max() == 0
+
+
+@pytest.fixture(scope="module")
+def full_size():
+    """BASELINE config: 2M surfels, 1600x1060, precomputed colours."""
+    P, W, H = 2_000_000, 1600, 1060
+    sc = synth.make_scene(P, W, H, seed=0)
+    gc, go = synth.make_upstream_grads(W, H, seed=1)
+    out = hz.run_product_surfel(sc, gc, go)
+    return sc, gc, go, out
+
+
+def test_full_size_identities(full_size):
+    sc, gc, go, out = full_size
+    C, O = out["color"].astype(np.float64), out["others"].astype(np.float64)
+    alpha = O[1]
+    assert alpha.min() >= 0 and alpha.max() <= 1.0 + 1e-6
+    assert np.isfinite(C).all() and np.isfinite(O).all()
+    assert (out["radii"] >= 0).all() and (out["radii"] > 0).mean() > 0.8
+    # C is linear in the colours: <dL/dcolours, colours> == <dL/dC, C - T*bg>   (bg = 0 here)
+    lhs = float((out["grads"]["colors"].astype(np.float64) * sc.colors).sum())
+    rhs = float((gc.astype(np.float64) * C).sum())
+    assert abs(lhs - rhs) <= 2e-4 * max(abs(lhs), abs(rhs), 1e-12), (lhs, rhs)
+    # normals: same identity through allmap[2:5]; per-Gaussian normal grads are internal, so
+    # check the median-depth channel instead: it equals the depth of the surf-idx Gaussian's plane
+    idx = O[7].astype(np.int64)
+    assert ((idx >= -1) & (idx < sc.P)).all()
+    assert ((idx >= 0) == (O[5] > 0)).mean() > 0.999
+
+
+def test_full_size_background_linearity(full_size):
+    """color(bg) - color(0) == T * bg exactly through the same blend."""
+    sc, gc, go, out = full_size
+    sc2 = synth.make_scene(sc.P, sc.cam.W, sc.cam.H, seed=0, bg=(0.5, 0.25, 1.0))
+    out2 = hz.run_product_surfel(sc2)
+    T = 1.0 - out["others"][1].astype(np.float64)
+    for c in range(3):
+        d = out2["color"][c].astype(np.float64) - out["color"][c]
+        assert np.abs(d - T * float(sc2.cam.bg[c])).max() <= 2e-6
