@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -155,12 +155,16 @@ def run_ours(args, rank, world, device):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(dev)
-    barrier()
+    # the clock sampler starts BEFORE the warm-up so that nvidia-smi's own start-up (driver
+    # attach, ~0.5 s) is over when the timed region begins; it keeps sampling through both
+    # timed regions.
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
     if rank == 0:
         sampler.start()
+        time.sleep(1.0)
+    for _ in range(args.warmup):
+        step(dev)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

@@ -52,7 +52,8 @@ def check_forward(out, gold):
             (f"others[{c}]", out["others"][c], gold["others"][c]) for c in range(7)]:
         tol = DIST_TOL if name == "others[6]" else FWD_TOL
         assert hz.rel_linf(a, b, 1e-3) <= tol, name
-        assert hz.rel_linf(a, b) <= FWD_RAW_TOL, name
+        if name != "others[5]":  # median depth is a selection: a T > 0.5 flip swaps whole depths
+            assert hz.rel_linf(a, b) <= FWD_RAW_TOL, name
     # surf idx (channel 7) and median normal (8..10): identical except on flipped pixels
     assert (out["others"][7] != gold["others"][7]).mean() <= 2e-3
     for c in (8, 9, 10):

