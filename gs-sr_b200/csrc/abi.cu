@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include "common.cuh"
 #include "../../include/gsr_b200.h"
 
@@ -11,19 +12,19 @@ namespace gsr {
 // ---- kernels / helpers defined in the other translation units ---------------
 __global__ void surfel_preprocess_fwd(int, int, int, const float*, const float2*, const float4*, const float*,
                                       const float*, const float*, const bool, const ViewParams, const bool,
-                                      const bool, int*, GeomRec*, float4*, uint32_t*, float*, uint8_t*, int*);
+                                      const bool, int*, GeomRec*, CullRec*, uint32_t*, float*, uint8_t*, int*);
 __global__ void surfel_preprocess_bwd(int, int, int, const float*, const float2*, const float4*, const float*,
                                       const bool, const ViewParams, const int, const int, const int*,
                                       const GeomRec*, const uint8_t*, const float*, float*, float*, float*,
                                       float*, float*, float*, float*, float*, float*);
 __global__ void mark_visible_kernel(int, const float*, const ViewParams, uint8_t*);
-__global__ void duplicate_with_keys(int, const GeomRec*, const int*, const uint32_t*, int, int, uint64_t*,
-                                    uint32_t*);
-__global__ void build_records(int, const uint64_t*, const uint32_t*, const GeomRec*, const float4*,
-                              const float*, int, SplatRec*, uint2*);
-__global__ void surfel_render_fwd(const uint2*, const SplatRec*, int, int, int, const float*, float*,
+__global__ void duplicate_with_keys(int, const GeomRec*, const CullRec*, const int*, const uint32_t*, int, int,
+                                    uint64_t*, uint32_t*);
+__global__ void build_records(int, const uint64_t*, const uint32_t*, const GeomRec*, const CullRec*,
+                              const float*, int, int, int, float4*, size_t, uint2*);
+__global__ void surfel_render_fwd(const uint2*, const float4*, size_t, int, int, int, const float*, float*,
                                   uint32_t*, float*, float*);
-__global__ void surfel_render_bwd(const uint2*, const SplatRec*, int, int, int, const float*,
+__global__ void surfel_render_bwd(const uint2*, const float4*, size_t, int, int, int, const float*,
                                   const float*, const uint32_t*, const float*, const float*, float*);
 size_t scan_temp_bytes(int P);
 cudaError_t inclusive_scan(char*, size_t, const uint32_t*, uint32_t*, int, cudaStream_t);
@@ -45,7 +46,7 @@ size_t GeomWs::carve(GeomWs& w, char* base, int P, size_t scan_bytes) {
     Carver c(base);
     size_t n = P > 0 ? (size_t)P : 1;
     w.geom = c.take<GeomRec>(n);
-    w.cbox = c.take<float4>(n);
+    w.cull = c.take<CullRec>(n);
     w.tiles = c.take<uint32_t>(n);
     w.offsets = c.take<uint32_t>(n);
     w.rgb = c.take<float>(3 * n);
@@ -71,7 +72,8 @@ size_t BinWs::carve(BinWs& w, char* base, int64_t R, int P, size_t sort_bytes) {
     w.keys = c.take<uint64_t>(n);
     w.vals_unsorted = c.take<uint32_t>(n);
     w.vals = c.take<uint32_t>(n);
-    w.recs = c.take<SplatRec>(n);
+    w.plane_stride = (n + 7) & ~size_t(7);
+    w.planes = c.take<float4>(w.plane_stride * REC_PLANES);
     w.gacc = c.take<float>((size_t)(P > 0 ? P : 1) * GACC_STRIDE);
     w.sort_tmp = c.take<char>(sort_bytes);
     w.sort_tmp_bytes = sort_bytes;
@@ -104,6 +106,26 @@ static bool no_cull() {
     if (g_no_cull < 0) { const char* e = getenv("GSR_NO_CULL"); g_no_cull = (e && e[0] == '1') ? 1 : 0; }
     return g_no_cull == 1;
 }
+
+// ---- host-side stage timing to stderr (GSR_HOST_TIMING=1; developer aid) ----
+struct HostTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    char buf[512]; int len = 0;
+    HostTimer() {
+        static int v = -1;
+        if (v < 0) { const char* e = getenv("GSR_HOST_TIMING"); v = (e && e[0] == '1') ? 1 : 0; }
+        on = v == 1; t0 = std::chrono::steady_clock::now();
+    }
+    void mark(const char* name) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        len += snprintf(buf + len, sizeof(buf) - len, " %s=%.0fus", name,
+                        std::chrono::duration<double, std::micro>(t1 - t0).count());
+        t0 = t1;
+    }
+    void flush(const char* what) { if (on) fprintf(stderr, "[gsr host] %s:%s\n", what, buf); }
+};
 
 // ---- per-kernel device timing (cudaEvents on the caller's stream, off by default) ----
 // bench.py needs the dominant kernel's duration measured live, outside any profiler.
@@ -176,6 +198,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     const int W = width, H = height;
     const size_t N = (size_t)W * H;
 
+    HostTimer ht;
     const ViewParams vc = make_view(viewmatrix, projmatrix, cam_pos, W, H, scale_modifier);
     const int ntiles = vc.gx * vc.gy;
 
@@ -185,6 +208,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     if (!ibase) { set_error("imageBuffer callback failed (%zu bytes)", ibytes); return GSR_E_ALLOC; }
     ImageWs::carve(iw, align256(ibase), W, H);
     GSR_CUDA_CHECK(cudaMemsetAsync(iw.ranges, 0, (size_t)ntiles * sizeof(uint2), s));
+    ht.mark("imgbuf");
 
     int R = 0;
     GeomWs gw;
@@ -196,12 +220,13 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         char* gbase = geometryBuffer(user, gbytes);
         if (!gbase) { set_error("geometryBuffer callback failed (%zu bytes)", gbytes); return GSR_E_ALLOC; }
         GeomWs::carve(gw, align256(gbase), P, scan_bytes);
+        ht.mark("geombuf");
         GSR_CUDA_CHECK(cudaMemsetAsync(gw.flags, 0, 32 * sizeof(int), s));
 
         prof_begin(GSR_PROF_PREPROCESS_FWD, s);
         surfel_preprocess_fwd<<<(P + 255) / 256, 256, 0, s>>>(
             P, D, M, means3D, (const float2*)scales, (const float4*)rotations, opacities, shs, transMat_precomp,
-            colors_precomp != nullptr, vc, prefiltered != 0, no_cull(), radii, gw.geom, gw.cbox, gw.tiles,
+            colors_precomp != nullptr, vc, prefiltered != 0, no_cull(), radii, gw.geom, gw.cull, gw.tiles,
             gw.rgb, gw.clamped, gw.flags);
         prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
@@ -212,12 +237,14 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         // (S/rasterizer_impl.cu:282), plus the prefiltered flag.
         uint32_t Ru = 0;
         int flag = 0;
+        ht.mark("launch_pre");
         GSR_CUDA_CHECK(cudaMemcpyAsync(&Ru, gw.offsets + (P - 1), 4, cudaMemcpyDeviceToHost, s));
         GSR_CUDA_CHECK(cudaMemcpyAsync(&flag, gw.flags, 4, cudaMemcpyDeviceToHost, s));
         GSR_CUDA_CHECK(cudaStreamSynchronize(s));
         if (flag) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
         if (Ru > 0x7fffff00u) { set_error("num_rendered overflow (%u)", Ru); return GSR_E_OVERFLOW; }
         R = (int)Ru;
+        ht.mark("sync_R");
     }
 
     size_t sort_bytes = R > 0 ? sort_temp_bytes(R) : 0;
@@ -225,10 +252,11 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     char* bbase = binningBuffer(user, bbytes);
     if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
     BinWs::carve(bw, align256(bbase), R, P, sort_bytes);
+    ht.mark("binbuf");
 
     if (R > 0) {
         prof_begin(GSR_PROF_DUPLICATE, s);
-        duplicate_with_keys<<<(P + 255) / 256, 256, 0, s>>>(P, gw.geom, radii, gw.offsets, vc.gx, vc.gy,
+        duplicate_with_keys<<<(P + 255) / 256, 256, 0, s>>>(P, gw.geom, gw.cull, radii, gw.offsets, vc.gx, vc.gy,
                                                             bw.keys_unsorted, bw.vals_unsorted);
         prof_end(GSR_PROF_DUPLICATE, s);
         GSR_CUDA_CHECK(cudaGetLastError());
@@ -239,17 +267,19 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         prof_end(GSR_PROF_SORT, s);
         const float* colors = colors_precomp ? colors_precomp : gw.rgb;
         prof_begin(GSR_PROF_BUILD_RECORDS, s);
-        build_records<<<(R + 255) / 256, 256, 0, s>>>(R, bw.keys, bw.vals, gw.geom, gw.cbox, colors, vc.gx,
-                                                      bw.recs, iw.ranges);
+        build_records<<<(R + 255) / 256, 256, 0, s>>>(R, bw.keys, bw.vals, gw.geom, gw.cull, colors, vc.gx, W, H,
+                                                      bw.planes, bw.plane_stride, iw.ranges);
         prof_end(GSR_PROF_BUILD_RECORDS, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }
     prof_begin(GSR_PROF_RENDER_FWD, s);
-    surfel_render_fwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.recs, W, H, vc.gx, background,
+    surfel_render_fwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.planes, bw.plane_stride, W, H, vc.gx, background,
                                                   iw.final_T, iw.n_contrib, out_color, out_others);
     prof_end(GSR_PROF_RENDER_FWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
     (void)N;
+    ht.mark("launch_rest");
+    ht.flush("forward");
     if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return R;
 }
@@ -285,7 +315,7 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
     GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * GACC_STRIDE * sizeof(float), s));
     if (R > 0) {
         prof_begin(GSR_PROF_RENDER_BWD, s);
-        surfel_render_bwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.recs, W, H, vc.gx, background,
+        surfel_render_bwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.planes, bw.plane_stride, W, H, vc.gx, background,
                                                       iw.final_T, iw.n_contrib, dL_dpix, dL_dothers,
                                                       bw.gacc);
         prof_end(GSR_PROF_RENDER_BWD, s);

@@ -45,32 +45,35 @@ struct __align__(16) GeomRec {
     float4 nd;  // view-space normal (facing the camera),           view depth
 };
 
-// Per-(Gaussian, tile) record, materialised in sorted (tile, depth, index) order
-// so that each tile's list is one contiguous 80-byte-stride stream that a CTA
-// pulls into shared memory with cp.async.bulk.  Homography rows and the filter
-// centre are re-expressed in TILE-LOCAL pixel coordinates (origin = tile's first pixel).
-struct __align__(16) SplatRec {
-    float4 tu;   // Tu - ox*Tw,   cx - ox
-    float4 tv;   // Tv - oy*Tw,   cy - oy
-    float4 tw;   // Tw,           opacity
-    float4 ng;   // normal.xyz,   Gaussian index (int bits)
-    float4 cb;   // colour rgb,   packed conservative pixel bounds (int bits, see pack_bounds)
+// Per-Gaussian culling record (forward preprocess -> tile binning / record build).
+// The conic q (see cull.cuh) is expressed in a frame shifted to the splat's rounded
+// screen centre (sx, sy) so that its float32 coefficients stay well conditioned.
+struct __align__(16) CullRec {
+    float4 q0;  // xx, xy, yy, bx
+    float4 q1;  // by, c0, disc radius^2 (= tau/2), tau
+    float4 q2;  // sx, sy, mode (0 exact, 1 always evaluate, 2 never), unused
 };
-static_assert(sizeof(SplatRec) == 80, "SplatRec must be 80 bytes");
+constexpr int CULL_EXACT = 0, CULL_ALWAYS = 1, CULL_NEVER = 2;
 
-// Per-Gaussian gradient accumulator filled by the backward render (float atomics
-// after in-warp reduction), consumed by the backward preprocess.  80 bytes.
-//   [0..8] dL/dT (Tu,Tv,Tw)  [9..11] dL/dcolour  [12..14] dL/dnormal  [15] dL/dopacity
-//   [16..17] dL/d(filter centre)  [18..19] pad
+// Per-(Gaussian, tile) record stream, materialised in sorted (tile, depth, index) order as
+// SIX float4 planes (SoA of 16-byte words): each tile's list is a contiguous run in every
+// plane, pulled into shared memory with cp.async.bulk, and lane j's 128-bit read of entry j
+// is bank-conflict free.  All geometry is in TILE-LOCAL pixel coordinates (origin = the
+// tile's first pixel): with Tu' = Tu - ox Tw, Tv' = Tv - oy Tw,
+//     p(x,y) = k x l = a x + b y + c,  a = Tv' x Tw,  b = Tw x Tu',  c = Tu' x Tv',
+//     s = p.xy / p.z,   depth = s.Tw.xy + Tw.z = det(T) / p.z.
+//   plane 0 (QA): a.xyz, cx'           plane 3 (QD): det(T), tau, Tw.z, index | flag<<31
+//   plane 1 (QB): b.xyz, cy'           plane 4 (PN): normal.xyz, colour.r
+//   plane 2 (QC): c.xyz, opacity       plane 5 (PC): colour.g, colour.b, sx', sy' (moment origin)
+constexpr int REC_PLANES = 6;
+constexpr uint32_t REC_FLAG_ALWAYS = 0x80000000u;   // conic is not an ellipse: evaluate on every pixel
+
+// Per-Gaussian gradient accumulator filled by the backward render (float atomics after the
+// in-warp reduction), consumed by the backward preprocess.  80 bytes:
+//   [0..2] M0 = sum dL/dp      [3..5] MX = sum x~ dL/dp    [6..8] MY = sum y~ dL/dp   (x~,y~ from the moment origin)
+//   [9] dL/d det(T)            [10..12] dL/dcolour         [13..15] dL/dnormal
+//   [16] dL/dopacity           [17] dL/dTw.z (low-pass branch)   [18..19] dL/d(filter centre)
 constexpr int GACC_STRIDE = 20;
-
-// bounds: local pixel range [xmin,xmax] x [ymin,ymax] (each 0..15) outside of which
-// the splat provably cannot reach alpha >= 1/255; bit 16 set = empty.
-__host__ __device__ inline uint32_t pack_bounds(int xmin, int xmax, int ymin, int ymax) {
-    return (uint32_t)xmin | ((uint32_t)xmax << 4) | ((uint32_t)ymin << 8) | ((uint32_t)ymax << 12);
-}
-constexpr uint32_t BOUNDS_EMPTY = 1u << 16;
-constexpr uint32_t BOUNDS_FULL = 0u | (15u << 4) | (0u << 8) | (15u << 12);
 
 // ---- workspace carving (128-byte aligned sub-allocations of one blob) -------
 struct Carver {
@@ -87,7 +90,7 @@ struct Carver {
 
 struct GeomWs {      // geometryBuffer
     GeomRec* geom;       // P
-    float4* cbox;        // P  conservative contribution box, global pixel coords (xmin,xmax,ymin,ymax)
+    CullRec* cull;       // P
     uint32_t* tiles;     // P  tiles touched
     uint32_t* offsets;   // P  inclusive scan
     float* rgb;          // 3P (SH path only; else unused)
@@ -110,7 +113,8 @@ struct BinWs {       // binningBuffer
     uint64_t* keys;
     uint32_t* vals_unsorted;
     uint32_t* vals;
-    SplatRec* recs;      // R
+    float4* planes;      // REC_PLANES x Rpad float4 (plane stride = Rpad)
+    size_t plane_stride; // Rpad = R rounded up to a multiple of 8 (keeps every plane 128-byte aligned)
     float* gacc;         // P * GACC_STRIDE (backward accumulators; lives here so forward owns one blob)
     char* sort_tmp;
     size_t sort_tmp_bytes;
@@ -149,6 +153,12 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
     return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// Origin of the backward's moment frame along one axis: the splat's screen centre, clamped to
+// the image and rounded (exactly reproducible in build_records and preprocess_bwd).
+__device__ __forceinline__ float moment_origin(float c, int extent) {
+    return rintf(fminf(fmaxf(c, 0.f), (float)(extent - 1)));
+}
 
 // S/cuda_rasterizer/auxiliary.h:69-79 (getRect); r is the integer radius.
 __device__ __forceinline__ void get_rect(float px, float py, int r, int gx, int gy, int& x0, int& y0,

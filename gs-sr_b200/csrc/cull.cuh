@@ -1,0 +1,152 @@
+// cull.cuh -- conservative "can this splat reach alpha >= 1/255 anywhere in this pixel
+// rectangle?" test, shared by tile binning (16x16 tiles) and the render kernels (8x4 warp blocks).
+//
+// A surfel contributes to pixel (x,y) only if (S/cuda_rasterizer/forward.cu:351-389)
+//      alpha = min(.99, o * exp(-rho/2)) >= 1/255,  rho = min(rho3d, rho2d)
+//   <=> rho <= tau := 2 ln(255 o)
+//   <=> (x,y) in  E = { rho3d <= tau }  or  (x,y) in  Dsc = { |(x,y) - c|^2 <= tau/2 }.
+// With p(x,y) = a x + b y + c0 (adjugate rows of the splat->pixel homography) the ray-splat
+// intersection is s = p.xy / p.z, so  rho3d <= tau  <=>  q(x,y) = p.x^2 + p.y^2 - tau p.z^2 <= 0:
+// a conic.  When its quadratic part is positive definite it is an ellipse and the test below is
+// exact for the continuous rectangle (hence conservative for the pixel centres inside it);
+// otherwise (the tau-disc of the splat reaches the camera plane) the caller must treat the
+// splat as "always evaluate".  tau carries slack for exp/log rounding and the rectangle is
+// widened by a quarter pixel, orders of magnitude above the float32 evaluation error.
+#pragma once
+#include "common.cuh"
+
+namespace gsr {
+
+constexpr float CULL_MARGIN = 0.25f;
+
+struct Quadric {           // q(x,y) = xx x^2 + 2 xy x y + yy y^2 + 2 bx x + 2 by y + c0
+    float xx, xy, yy, bx, by, c0;
+};
+
+// tau (with slack) for an opacity; < 0 means the splat can never reach 1/255.
+__device__ __forceinline__ float contribution_tau(float opacity) {
+    float a = 255.0f * opacity;
+    if (!(a >= 1.0f)) return -1.0f;
+    return 2.0f * __logf(a) * 1.001f + 2e-3f;
+}
+
+__device__ __forceinline__ Quadric make_quadric(float3 a, float3 b, float3 c, float tau) {
+    Quadric q;
+    q.xx = a.x * a.x + a.y * a.y - tau * a.z * a.z;
+    q.xy = a.x * b.x + a.y * b.y - tau * a.z * b.z;
+    q.yy = b.x * b.x + b.y * b.y - tau * b.z * b.z;
+    q.bx = a.x * c.x + a.y * c.y - tau * a.z * c.z;
+    q.by = b.x * c.x + b.y * c.y - tau * b.z * c.z;
+    q.c0 = c.x * c.x + c.y * c.y - tau * c.z * c.z;
+    return q;
+}
+
+// true when the quadratic part is safely positive definite (ellipse)
+__device__ __forceinline__ bool quadric_is_ellipse(const Quadric& q) {
+    float det = q.xx * q.yy - q.xy * q.xy;
+    return (q.xx > 0.f) && (q.yy > 0.f) && (det > 1e-6f * q.xx * q.yy);
+}
+
+__device__ __forceinline__ float quadric_eval(const Quadric& q, float x, float y) {
+    return (q.xx * x + 2.f * (q.xy * y + q.bx)) * x + (q.yy * y + 2.f * q.by) * y + q.c0;
+}
+
+// Ellipse {q <= 0} vs rectangle [x0,x1]x[y0,y1]; requires quadric_is_ellipse(q).
+__device__ __forceinline__ bool ellipse_hits_rect(const Quadric& q, float x0, float x1, float y0, float y1) {
+    const float det = q.xx * q.yy - q.xy * q.xy;            // > 0
+    // centre e solves [xx xy; xy yy] e = -(bx, by); compare without dividing
+    const float ex = q.xy * q.by - q.yy * q.bx, ey = q.xy * q.bx - q.xx * q.by;   // = det * centre
+    if (ex >= x0 * det && ex <= x1 * det && ey >= y0 * det && ey <= y1 * det) return true;
+    // corners
+    if (quadric_eval(q, x0, y0) <= 0.f || quadric_eval(q, x1, y0) <= 0.f || quadric_eval(q, x0, y1) <= 0.f ||
+        quadric_eval(q, x1, y1) <= 0.f) return true;
+    // edges: interior minimum of the 1-D restriction  t -> A t^2 + 2 B t + C  is C - B^2/A at t* = -B/A
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float yc = k ? y1 : y0;
+        const float B = q.xy * yc + q.bx, C = (q.yy * yc + 2.f * q.by) * yc + q.c0;
+        if (-B > x0 * q.xx && -B < x1 * q.xx && C * q.xx <= B * B) return true;
+        const float xc = k ? x1 : x0;
+        const float B2 = q.xy * xc + q.by, C2 = (q.xx * xc + 2.f * q.bx) * xc + q.c0;
+        if (-B2 > y0 * q.yy && -B2 < y1 * q.yy && C2 * q.yy <= B2 * B2) return true;
+    }
+    return false;
+}
+
+// Disc of squared radius r2 around (cx,cy) vs rectangle.
+__device__ __forceinline__ bool disc_hits_rect(float cx, float cy, float r2, float x0, float x1, float y0, float y1) {
+    const float dx = fmaxf(fmaxf(x0 - cx, cx - x1), 0.f), dy = fmaxf(fmaxf(y0 - cy, cy - y1), 0.f);
+    return dx * dx + dy * dy <= r2;
+}
+
+// Culling record of one Gaussian: conic of {rho3d <= tau} in a frame shifted to the rounded
+// screen centre (keeps the float32 coefficients well conditioned), low-pass disc radius, mode.
+__device__ __forceinline__ CullRec make_cull_rec(float3 Tu, float3 Tv, float3 Tw, float cx, float cy,
+                                                 float opacity, bool no_cull) {
+    CullRec r;
+    const float sx = rintf(cx), sy = rintf(cy);
+    float tau = contribution_tau(opacity);
+    int mode = CULL_EXACT;
+    Quadric q = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (no_cull) { mode = CULL_ALWAYS; tau = fmaxf(tau, 0.f); }
+    else if (tau < 0.f) { mode = CULL_NEVER; tau = 0.f; }
+    else {
+        const float3 tu = make_float3(fmaf(-sx, Tw.x, Tu.x), fmaf(-sx, Tw.y, Tu.y), fmaf(-sx, Tw.z, Tu.z));
+        const float3 tv = make_float3(fmaf(-sy, Tw.x, Tv.x), fmaf(-sy, Tw.y, Tv.y), fmaf(-sy, Tw.z, Tv.z));
+        q = make_quadric(cross3(tv, Tw), cross3(Tw, tu), cross3(tu, tv), tau);
+        const bool finite = fabsf(q.xx) < 3e38f && fabsf(q.yy) < 3e38f && fabsf(q.c0) < 3e38f &&
+                            fabsf(sx) < 1e7f && fabsf(sy) < 1e7f;
+        if (!finite || !quadric_is_ellipse(q)) mode = CULL_ALWAYS;
+    }
+    r.q0 = make_float4(q.xx, q.xy, q.yy, q.bx);
+    r.q1 = make_float4(q.by, q.c0, 0.5f * tau, tau);
+    r.q2 = make_float4(sx, sy, (float)mode, 0.f);
+    return r;
+}
+
+// ---- tile-level test -------------------------------------------------------------------
+// The forward preprocess COUNTS tiles with tile_may_contribute and duplicate_with_keys EMITS
+// with it; both must take bit-identical decisions although they are inlined into different
+// kernels.  Every operation below is therefore an explicit round-to-nearest intrinsic
+// (__fmul_rn/__fadd_rn/__fmaf_rn are never contracted or re-associated by the compiler).
+__device__ __forceinline__ float det_eval_rn(float xx, float xy, float yy, float bx, float by, float c0, float x, float y) {
+    // (xx x + 2 (xy y + bx)) x + (yy y + 2 by) y + c0
+    const float t0 = __fmaf_rn(xx, x, __fmul_rn(2.f, __fmaf_rn(xy, y, bx)));
+    const float t1 = __fmaf_rn(yy, y, __fmul_rn(2.f, by));
+    return __fadd_rn(__fmaf_rn(t0, x, __fmul_rn(t1, y)), c0);
+}
+
+__device__ __forceinline__ bool tile_may_contribute(const CullRec& r, float cx, float cy, int tx, int ty) {
+    const int mode = (int)r.q2.z;
+    if (mode == CULL_ALWAYS) return true;
+    if (mode == CULL_NEVER) return false;
+    const float gx0 = __fadd_rn((float)(tx * TILE), -CULL_MARGIN), gx1 = __fadd_rn((float)(tx * TILE + TILE - 1), CULL_MARGIN);
+    const float gy0 = __fadd_rn((float)(ty * TILE), -CULL_MARGIN), gy1 = __fadd_rn((float)(ty * TILE + TILE - 1), CULL_MARGIN);
+    {   // low-pass disc
+        const float dx = fmaxf(fmaxf(__fadd_rn(gx0, -cx), __fadd_rn(cx, -gx1)), 0.f);
+        const float dy = fmaxf(fmaxf(__fadd_rn(gy0, -cy), __fadd_rn(cy, -gy1)), 0.f);
+        if (__fmaf_rn(dx, dx, __fmul_rn(dy, dy)) <= r.q1.z) return true;
+    }
+    const float xx = r.q0.x, xy = r.q0.y, yy = r.q0.z, bx = r.q0.w, by = r.q1.x, c0 = r.q1.y;
+    const float x0 = __fadd_rn(gx0, -r.q2.x), x1 = __fadd_rn(gx1, -r.q2.x);
+    const float y0 = __fadd_rn(gy0, -r.q2.y), y1 = __fadd_rn(gy1, -r.q2.y);
+    const float det = __fmaf_rn(xx, yy, -__fmul_rn(xy, xy));
+    const float ex = __fmaf_rn(xy, by, -__fmul_rn(yy, bx)), ey = __fmaf_rn(xy, bx, -__fmul_rn(xx, by));
+    if (ex >= __fmul_rn(x0, det) && ex <= __fmul_rn(x1, det) && ey >= __fmul_rn(y0, det) && ey <= __fmul_rn(y1, det)) return true;
+    if (det_eval_rn(xx, xy, yy, bx, by, c0, x0, y0) <= 0.f || det_eval_rn(xx, xy, yy, bx, by, c0, x1, y0) <= 0.f ||
+        det_eval_rn(xx, xy, yy, bx, by, c0, x0, y1) <= 0.f || det_eval_rn(xx, xy, yy, bx, by, c0, x1, y1) <= 0.f) return true;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float yc = k ? y1 : y0;
+        const float B = __fmaf_rn(xy, yc, bx);
+        const float C = __fadd_rn(__fmul_rn(__fmaf_rn(yy, yc, __fmul_rn(2.f, by)), yc), c0);
+        if (-B > __fmul_rn(x0, xx) && -B < __fmul_rn(x1, xx) && __fmul_rn(C, xx) <= __fmul_rn(B, B)) return true;
+        const float xc = k ? x1 : x0;
+        const float B2 = __fmaf_rn(xy, xc, by);
+        const float C2 = __fadd_rn(__fmul_rn(__fmaf_rn(xx, xc, __fmul_rn(2.f, bx)), xc), c0);
+        if (-B2 > __fmul_rn(y0, yy) && -B2 < __fmul_rn(y1, yy) && __fmul_rn(C2, yy) <= __fmul_rn(B2, B2)) return true;
+    }
+    return false;
+}
+
+}  // namespace gsr

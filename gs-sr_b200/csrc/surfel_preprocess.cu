@@ -13,6 +13,7 @@
 // (zeros for culled Gaussians), so no output needs a memset.
 #include "common.cuh"
 #include "sh.cuh"
+#include "cull.cuh"
 #include "../../include/gsr_b200.h"
 
 namespace gsr {
@@ -31,37 +32,48 @@ __device__ __forceinline__ void quat_to_rot(float4 q, float3& c0, float3& c1, fl
     c2 = make_float3(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
 }
 
-// Conservative box (global pixel coords) outside of which alpha < 1/255 for sure.
-//   alpha = min(.99, o * exp(-rho/2)) >= 1/255  <=>  rho <= tau = 2 ln(255 o),
-//   rho = min(rho3d, rho2d): union of the disc |pix - c|^2 <= tau/2 around the filter
-//   centre and of the projected ellipse rho3d <= tau (same closed form as
-//   compute_aabb with cutoff^2 = tau).  When the tau-disc of the splat reaches
-//   the camera plane (d >= 0) the projection is not an ellipse: return "everything".
-__device__ __forceinline__ float4 contribution_box(float3 Tu, float3 Tv, float3 Tw, float cx,
-                                                   float cy, float opacity) {
-    const float BIG = 3.0e38f;
-    float a = 255.0f * opacity;
-    if (!(a >= 1.0f)) return make_float4(BIG, -BIG, BIG, -BIG);  // can never reach 1/255 (also NaN-safe: empty)
-    float tau = 2.0f * logf(a) * 1.001f + 1e-3f;                 // slack for float rounding of exp/log
-    float r2 = sqrtf(0.5f * tau);
-    float x0 = cx - r2, x1 = cx + r2, y0 = cy - r2, y1 = cy + r2;
-    float ww = Tw.z * Tw.z;
-    float d = tau * (Tw.x * Tw.x + Tw.y * Tw.y) - ww;
-    if (!(d < -1e-4f * ww)) return make_float4(-BIG, BIG, -BIG, BIG);
-    float inv = 1.0f / d;
-    float fx = tau * inv, fz = -inv;
-    float ex = fx * (Tu.x * Tw.x + Tu.y * Tw.y) + fz * Tu.z * Tw.z;
-    float ey = fx * (Tv.x * Tw.x + Tv.y * Tw.y) + fz * Tv.z * Tw.z;
-    float hx2 = ex * ex - (fx * (Tu.x * Tu.x + Tu.y * Tu.y) + fz * Tu.z * Tu.z);
-    float hy2 = ey * ey - (fx * (Tv.x * Tv.x + Tv.y * Tv.y) + fz * Tv.z * Tv.z);
-    if (!(hx2 >= 0.f) || !(hy2 >= 0.f) || !(fabsf(ex) < 1e9f) || !(fabsf(ey) < 1e9f))
-        return make_float4(-BIG, BIG, -BIG, BIG);
-    // relative slack for cancellation in h^2 (terms of magnitude e^2)
-    float hx = sqrtf(hx2 + 1e-4f * (ex * ex + 1.f)), hy = sqrtf(hy2 + 1e-4f * (ey * ey + 1.f));
-    x0 = fminf(x0, ex - hx); x1 = fmaxf(x1, ex + hx);
-    y0 = fminf(y0, ey - hy); y1 = fmaxf(y1, ey + hy);
-    const float m = 0.5f;  // half-pixel safety margin
-    return make_float4(x0 - m, x1 + m, y0 - m, y1 + m);
+// ---- pinned float32 sequences ------------------------------------------------------------
+// radius = ceil(sqrt(p^2 - f.(T o T))) cancels ~4 digits in global pixel coordinates and the
+// sort key is the raw bits of the view depth, so radii / tile lists / ordering only match the
+// reference if T, the AABB and p_view are rounded EXACTLY as its build rounds them.  The
+// sequences below were read off the SASS nvcc 12.9 emits for the unmodified reference
+// (cuobjdump of oracle/_ref/libref_surfel.so): every  a*x + b*y + c*z (+ d)  is evaluated as
+//     fma(c, z, fma(a, x, rn(b*y)))  (+ d with a separate add),
+// and explicit intrinsics keep the compiler from re-contracting them here.
+__device__ __forceinline__ float dot_yxz(float a, float x, float b, float y, float c, float z) {
+    return __fmaf_rn(c, z, __fmaf_rn(a, x, __fmul_rn(b, y)));
+}
+__device__ __forceinline__ float3 xform43_pinned(const float* __restrict__ m, float3 p) {
+    return make_float3(__fadd_rn(dot_yxz(p.x, m[0], p.y, m[4], p.z, m[8]), m[12]),
+                       __fadd_rn(dot_yxz(p.x, m[1], p.y, m[5], p.z, m[9]), m[13]),
+                       __fadd_rn(dot_yxz(p.x, m[2], p.y, m[6], p.z, m[10]), m[14]));
+}
+__device__ __forceinline__ float3 xformvec43_pinned(const float* __restrict__ m, float3 p) {
+    return make_float3(dot_yxz(p.x, m[0], p.y, m[4], p.z, m[8]), dot_yxz(p.x, m[1], p.y, m[5], p.z, m[9]),
+                       dot_yxz(p.x, m[2], p.y, m[6], p.z, m[10]));
+}
+// quat (w,x,y,z) -> rotation columns, S/auxiliary.h:215-237, in the reference build's rounding
+__device__ __forceinline__ void quat_to_rot_pinned(float4 q, float3& c0, float3& c1, float3& c2) {
+    const float sum = __fmaf_rn(q.z, q.z, __fmaf_rn(q.y, q.y, __fmaf_rn(q.x, q.x, __fmul_rn(q.w, q.w))));
+    const float s = rsqrtf(sum);
+    const float w = __fmul_rn(q.x, s), x = __fmul_rn(q.y, s), y = __fmul_rn(q.z, s), z = __fmul_rn(q.w, s);
+    const float wz = __fmul_rn(w, z), wx = __fmul_rn(w, x), wy = __fmul_rn(w, y);
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    const float t00 = __fadd_rn(yy, zz), t11 = __fmaf_rn(x, x, zz), t22 = __fmaf_rn(x, x, yy);
+    const float xy_p = __fmaf_rn(x, y, wz), xy_m = __fmaf_rn(x, y, -wz);
+    const float yz_p = __fmaf_rn(y, z, wx), yz_m = __fmaf_rn(y, z, -wx);
+    const float xz_p = __fmaf_rn(x, z, wy), xz_m = __fmaf_rn(x, z, -wy);
+    c0 = make_float3(__fadd_rn(1.f, -__fadd_rn(t00, t00)), __fadd_rn(xy_p, xy_p), __fadd_rn(xz_m, xz_m));
+    c1 = make_float3(__fadd_rn(xy_m, xy_m), __fadd_rn(1.f, -__fadd_rn(t11, t11)), __fadd_rn(yz_p, yz_p));
+    c2 = make_float3(__fadd_rn(xz_p, xz_p), __fadd_rn(yz_m, yz_m), __fadd_rn(1.f, -__fadd_rn(t22, t22)));
+}
+// one row of compute_aabb: centre c = f.(T o Tw), h^2 = c^2 - f.(T o T)   (f = (9,9,-1)/d)
+__device__ __forceinline__ void aabb_row_pinned(float3 T, float3 Tw, float f0, float invd, float& c, float& h2) {
+    const float mx = __fmul_rn(Tw.x, T.x), my = __fmul_rn(Tw.y, T.y), mz = __fmul_rn(Tw.z, T.z);
+    c = __fmaf_rn(mz, -invd, __fmaf_rn(f0, mx, __fmul_rn(f0, my)));
+    const float qx = __fmul_rn(T.x, T.x), qy = __fmul_rn(T.y, T.y), qz = __fmul_rn(T.z, T.z);
+    const float nd = __fmaf_rn(qz, invd, -__fmaf_rn(f0, qx, __fmul_rn(f0, qy)));
+    h2 = __fmaf_rn(c, c, nd);
 }
 
 __global__ void __launch_bounds__(256)
@@ -70,7 +82,7 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ opacities, const float* __restrict__ shs,
                       const float* __restrict__ transMat_precomp, const bool has_colors,
                       const ViewParams vc, const bool prefiltered, const bool no_cull,
-                      int* __restrict__ radii, GeomRec* __restrict__ geom, float4* __restrict__ cbox,
+                      int* __restrict__ radii, GeomRec* __restrict__ geom, CullRec* __restrict__ cull,
                       uint32_t* __restrict__ tiles, float* __restrict__ rgb,
                       uint8_t* __restrict__ clamped, int* __restrict__ flags) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,7 +93,7 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
     load16(vc.view, view);
     do {
         float3 p = make_float3(__ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1), __ldg(means3D + 3 * idx + 2));
-        float3 pv = xform43(view, p);
+        float3 pv = xform43_pinned(view, p);
         if (pv.z <= 0.2f) {  // in_frustum, S/auxiliary.h:187-212
             if (prefiltered) atomicExch(flags, 1);
             break;
@@ -89,27 +101,29 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
         float3 Tu, Tv, Tw, normal;
         if (transMat_precomp == nullptr) {
             float3 c0, c1, c2;
-            quat_to_rot(__ldg(rotations + idx), c0, c1, c2);
+            quat_to_rot_pinned(__ldg(rotations + idx), c0, c1, c2);
             float2 sc = __ldg(scales + idx);
-            float su = vc.scale_modifier * sc.x, sv = vc.scale_modifier * sc.y;
-            float3 L0 = make_float3(c0.x * su, c0.y * su, c0.z * su);
-            float3 L1 = make_float3(c1.x * sv, c1.y * sv, c1.z * sv);
-            // T = (splat2world^T * world2ndc) * ndc2pix in the reference's association order
+            const float su = __fmul_rn(sc.x, vc.scale_modifier), sv = __fmul_rn(sc.y, vc.scale_modifier);
+            const float3 L0 = make_float3(__fmul_rn(su, c0.x), __fmul_rn(su, c0.y), __fmul_rn(su, c0.z));
+            const float3 L1 = make_float3(__fmul_rn(sv, c1.x), __fmul_rn(sv, c1.y), __fmul_rn(sv, c1.z));
+            // T = (splat2world^T * world2ndc) * ndc2pix, S/forward.cu:93-112
             float pm[16];
             load16(vc.proj, pm);
-            float hw = 0.5f * (float)vc.W, hwm = 0.5f * (float)(vc.W - 1);
-            float hh = 0.5f * (float)vc.H, hhm = 0.5f * (float)(vc.H - 1);
+            const float hw = 0.5f * (float)vc.W, hwm = 0.5f * (float)(vc.W - 1);
+            const float hh = 0.5f * (float)vc.H, hhm = 0.5f * (float)(vc.H - 1);
             float cu[4], cv[4], cc[4];
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                cu[c] = L0.x * pm[c] + L0.y * pm[4 + c] + L0.z * pm[8 + c];
-                cv[c] = L1.x * pm[c] + L1.y * pm[4 + c] + L1.z * pm[8 + c];
-                cc[c] = p.x * pm[c] + p.y * pm[4 + c] + p.z * pm[8 + c] + pm[12 + c];
+                cu[c] = dot_yxz(L0.x, pm[c], L0.y, pm[4 + c], L0.z, pm[8 + c]);
+                cv[c] = dot_yxz(L1.x, pm[c], L1.y, pm[4 + c], L1.z, pm[8 + c]);
+                cc[c] = __fadd_rn(pm[12 + c], dot_yxz(p.x, pm[c], p.y, pm[4 + c], p.z, pm[8 + c]));
             }
-            Tu = make_float3(cu[0] * hw + cu[3] * hwm, cv[0] * hw + cv[3] * hwm, cc[0] * hw + cc[3] * hwm);
-            Tv = make_float3(cu[1] * hh + cu[3] * hhm, cv[1] * hh + cv[3] * hhm, cc[1] * hh + cc[3] * hhm);
+            Tu = make_float3(__fmaf_rn(hwm, cu[3], __fmul_rn(hw, cu[0])), __fmaf_rn(hwm, cv[3], __fmul_rn(hw, cv[0])),
+                             __fmaf_rn(hwm, cc[3], __fmul_rn(hw, cc[0])));
+            Tv = make_float3(__fmaf_rn(hhm, cu[3], __fmul_rn(hh, cu[1])), __fmaf_rn(hhm, cv[3], __fmul_rn(hh, cv[1])),
+                             __fmaf_rn(hhm, cc[3], __fmul_rn(hh, cc[1])));
             Tw = make_float3(cu[3], cv[3], cc[3]);
-            normal = xformvec43(view, c2);
+            normal = xformvec43_pinned(view, c2);
         } else {
             const float* t = transMat_precomp + 9 * (size_t)idx;
             Tu = make_float3(__ldg(t + 0), __ldg(t + 1), __ldg(t + 2));
@@ -118,21 +132,20 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
             normal = make_float3(0.f, 0.f, 1.f);
         }
         // DUAL_VISIABLE, S/forward.cu:209-214
-        float cosv = -(pv.x * normal.x + pv.y * normal.y + pv.z * normal.z);
+        const float cosv = -dot_yxz(pv.x, normal.x, pv.y, normal.y, pv.z, normal.z);
         if (cosv == 0.f) break;
-        float mult = cosv > 0.f ? 1.f : -1.f;
+        const float mult = cosv > 0.f ? 1.f : -1.f;
         normal = make_float3(mult * normal.x, mult * normal.y, mult * normal.z);
 
-        // compute_aabb with cutoff 3, S/forward.cu:119-145,223-231
-        float d = 9.0f * Tw.x * Tw.x + 9.0f * Tw.y * Tw.y - Tw.z * Tw.z;
+        // compute_aabb with cutoff 3, S/forward.cu:119-145,223-231 (pinned sequences above)
+        const float d = __fmaf_rn(-Tw.z, Tw.z, __fmaf_rn(__fmul_rn(Tw.x, Tw.x), 9.0f, __fmul_rn(__fmul_rn(Tw.y, Tw.y), 9.0f)));
         if (d == 0.0f) break;
-        float invd = 1.0f / d;
-        float f0 = invd * 9.0f, f2 = -invd;
-        float cx = f0 * Tu.x * Tw.x + f0 * Tu.y * Tw.y + f2 * Tu.z * Tw.z;
-        float cy = f0 * Tv.x * Tw.x + f0 * Tv.y * Tw.y + f2 * Tv.z * Tw.z;
-        float h0 = cx * cx - (f0 * Tu.x * Tu.x + f0 * Tu.y * Tu.y + f2 * Tu.z * Tu.z);
-        float h1 = cy * cy - (f0 * Tv.x * Tv.x + f0 * Tv.y * Tv.y + f2 * Tv.z * Tv.z);
-        float ex = sqrtf(fmaxf(1e-4f, h0)), ey = sqrtf(fmaxf(1e-4f, h1));
+        const float invd = __fdiv_rn(1.0f, d);
+        const float f0 = __fmul_rn(invd, 9.0f);
+        float cx, cy, h0, h1;
+        aabb_row_pinned(Tu, Tw, f0, invd, cx, h0);
+        aabb_row_pinned(Tv, Tw, f0, invd, cy, h1);
+        const float ex = sqrtf(fmaxf(1e-4f, h0)), ey = sqrtf(fmaxf(1e-4f, h1));
         float radius = ceilf(fmaxf(fmaxf(ex, ey), 3.0f * FILTER_SIZE));
         int ri = (int)radius;
         int x0, y0, x1, y1;
@@ -151,9 +164,14 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
         g.tw = make_float4(Tw.x, Tw.y, Tw.z, opa);
         g.nd = make_float4(normal.x, normal.y, normal.z, pv.z);
         geom[idx] = g;
-        cbox[idx] = no_cull ? make_float4(-3e38f, 3e38f, -3e38f, 3e38f) : contribution_box(Tu, Tv, Tw, cx, cy, opa);
+        const CullRec cr = make_cull_rec(Tu, Tv, Tw, cx, cy, opa, no_cull);
+        cull[idx] = cr;
         radius_out = ri;
-        tiles_out = (uint32_t)((y1 - y0) * (x1 - x0));
+        // tiles of the reference rect (S/auxiliary.h:69-79) that the splat can actually reach
+        uint32_t n = 0;
+        for (int ty = y0; ty < y1; ty++)
+            for (int tx = x0; tx < x1; tx++) n += tile_may_contribute(cr, cx, cy, tx, ty) ? 1u : 0u;
+        tiles_out = n;
     } while (0);
     radii[idx] = radius_out;
     tiles[idx] = tiles_out;
@@ -186,12 +204,16 @@ surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const float4* ga = reinterpret_cast<const float4*>(gacc + (size_t)idx * GACC_STRIDE);
-    float4 a0 = ga[0], a1 = ga[1], a2 = ga[2], a3 = ga[3], a4 = ga[4];
-    float dT[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
-    float3 dcol = make_float3(a2.y, a2.z, a2.w);
-    float3 dnrm = make_float3(a3.x, a3.y, a3.z);
-    float dopa = a3.w;
-    float dm2x = a4.x, dm2y = a4.y;
+    const float4 a0 = ga[0], a1 = ga[1], a2 = ga[2], a3 = ga[3], a4 = ga[4];
+    const float3 M0 = make_float3(a0.x, a0.y, a0.z), MX = make_float3(a0.w, a1.x, a1.y),
+                 MY = make_float3(a1.z, a1.w, a2.x);
+    const float dDet = a2.y;
+    float3 dcol = make_float3(a2.z, a2.w, a3.x);
+    float3 dnrm = make_float3(a3.y, a3.z, a3.w);
+    float dopa = a4.x;
+    const float dTwz_lowpass = a4.y;
+    float dm2x = a4.z, dm2y = a4.w;
+    float dT[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float3 dmean = make_float3(0.f, 0.f, 0.f);
     float2 dscale = make_float2(0.f, 0.f);
     float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -208,6 +230,28 @@ surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
     }
     if (visible) {
         GeomRec g = geom[idx];
+        {   // moments of dL/dp -> dL/dT (the linear part of S/backward.cu:413-421, once per Gaussian)
+            const float sx = moment_origin(g.tu.w, vc.W), sy = moment_origin(g.tv.w, vc.H);
+            const float3 tw = make_float3(g.tw.x, g.tw.y, g.tw.z);
+            const float3 tu = make_float3(fmaf(-sx, tw.x, g.tu.x), fmaf(-sx, tw.y, g.tu.y), fmaf(-sx, tw.z, g.tu.z));
+            const float3 tv = make_float3(fmaf(-sy, tw.x, g.tv.x), fmaf(-sy, tw.y, g.tv.y), fmaf(-sy, tw.z, g.tv.z));
+            const float3 A = cross3(tv, tw), B = cross3(tw, tu), C = cross3(tu, tv);   // cofactors = d det / dT
+            const float3 u1 = cross3(MY, tw), u2 = cross3(tv, M0);
+            const float3 v1 = cross3(tw, MX), v2 = cross3(M0, tu);
+            const float3 w1 = cross3(MX, tv), w2 = cross3(tu, MY);
+            const float3 dtu = make_float3(u1.x + u2.x + dDet * A.x, u1.y + u2.y + dDet * A.y, u1.z + u2.z + dDet * A.z);
+            const float3 dtv = make_float3(v1.x + v2.x + dDet * B.x, v1.y + v2.y + dDet * B.y, v1.z + v2.z + dDet * B.z);
+            const float3 dtw = make_float3(w1.x + w2.x + dDet * C.x, w1.y + w2.y + dDet * C.y,
+                                           w1.z + w2.z + dDet * C.z + dTwz_lowpass);
+            // Tu~ = Tu - sx Tw, Tv~ = Tv - sy Tw  =>  dTw = dTw~ - sx dTu~ - sy dTv~
+            dT[0] = dtu.x; dT[1] = dtu.y; dT[2] = dtu.z;
+            dT[3] = dtv.x; dT[4] = dtv.y; dT[5] = dtv.z;
+            dT[6] = dtw.x - sx * dtu.x - sy * dtv.x;
+            dT[7] = dtw.y - sx * dtu.y - sy * dtv.y;
+            dT[8] = dtw.z - sx * dtu.z - sy * dtv.z;
+#pragma unroll
+            for (int i = 0; i < 9; i++) dTout[i] = dT[i];
+        }
         float3 Tu, Tv, Tw, c0, c1, c2, normal = make_float3(0.f, 0.f, 0.f), p;
         float Pm[3][4];
         float2 sc = make_float2(0.f, 0.f);

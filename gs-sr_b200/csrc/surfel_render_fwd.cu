@@ -1,38 +1,38 @@
-// surfel_render_fwd.cu -- per-tile front-to-back alpha blend of 2D Gaussian
-// surfels (colour + 11 auxiliary channels) for sm_100a.
+// surfel_render_fwd.cu -- per-tile front-to-back alpha blend of 2D Gaussian surfels
+// (colour + 11 auxiliary channels) for sm_100a.
 //
 // Result contract = reference renderCUDA, S/cuda_rasterizer/forward.cu:256-448
-// (ray-splat intersection :351-368, low-pass :362-366, alpha :381-389,
-// distortion moments :395-400, median bookkeeping :402-408, outputs :427-447).
+// (ray-splat intersection :351-368, low-pass :362-366, alpha :381-389, distortion
+// moments :395-400, median bookkeeping :402-408, outputs :427-447).
 //
 // B200 design (not the reference's):
 //   * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block;
-//   * the tile's sorted SplatRec stream is contiguous in HBM: one elected
-//     thread pulls 128-record batches (10 KB) into a double-buffered shared
-//     ring with cp.async.bulk + mbarrier (SASS UBLKCP), overlapping the next
-//     batch's HBM/L2 latency with the current batch's blend;
-//   * each warp culls the batch 32 records at a time: lane j tests record j's
-//     conservative pixel bounds against the warp's 8x4 block, one ballot, and
-//     only the surviving records are evaluated (the culled pairs provably
-//     have alpha < 1/255, i.e. the reference would `continue` on them);
-//   * records carry tile-local homography rows, so pixel coordinates are small
-//     integers (better conditioned than the reference's global-pixel form);
-//   * a warp stops as soon as its 32 pixels are done (the reference waits for
-//     all 256), the CTA stops when all 8 warps have.
+//   * the tile's sorted record stream is contiguous in each of six float4 planes in HBM:
+//     one elected thread pulls 128-entry batches (6 x 2 KB cp.async.bulk, SASS UBLKCP) into
+//     a double-buffered shared ring guarded by mbarriers, overlapping the next batch's
+//     HBM/L2 latency with the current batch's blend;
+//   * the ray-splat intersection uses the adjugate rows stored in the record:
+//     p = a x + b y + c (6 FMA), s = p.xy / p.z, depth = det(T) / p.z -- algebraically the
+//     reference's k x l / (s.Tw) form, in tile-local coordinates (small integers);
+//   * each warp culls the batch 32 entries at a time: lane j tests entry j's conic
+//     {rho3d <= tau} and low-pass disc against the warp's 8x4 block (exact ellipse-vs-
+//     rectangle test, cull.cuh), one ballot, and only surviving entries are evaluated --
+//     the skipped pairs provably have alpha < 1/255 (the reference `continue`s on them);
+//   * MUFU rcp/ex2 approximations (1 ulp / 2^-22) replace IEEE division and expf;
+//   * a warp stops as soon as its 32 pixels are done (the reference waits for all 256).
 #include "common.cuh"
 #include "async_copy.cuh"
+#include "cull.cuh"
+#include "render_common.cuh"
 
 namespace gsr {
 
-constexpr int FWD_BATCH = 128;
-constexpr uint32_t FULLMASK = 0xffffffffu;
-
 __global__ void __launch_bounds__(TILE_PIX)
-surfel_render_fwd(const uint2* __restrict__ ranges, const SplatRec* __restrict__ recs, int W, int H,
-                  int gx, const float* __restrict__ bg, float* __restrict__ final_T,
+surfel_render_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ planes, size_t pstride, int W,
+                  int H, int gx, const float* __restrict__ bg, float* __restrict__ final_T,
                   uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                   float* __restrict__ out_others) {
-    __shared__ __align__(128) SplatRec sbuf[2][FWD_BATCH];
+    __shared__ __align__(128) float4 sbuf[2][REC_PLANES][RBATCH];
     __shared__ __align__(8) uint64_t full_bar[2];
 
     const int tile = blockIdx.x;
@@ -43,11 +43,14 @@ surfel_render_fwd(const uint2* __restrict__ ranges, const SplatRec* __restrict__
     const int px = tx * TILE + lx, py = ty * TILE + ly;
     const bool inside = px < W && py < H;
     const float fx = (float)lx, fy = (float)ly;
+    // warp block rectangle (continuous, widened) for the cull test
+    const float bx0 = (float)wx0 - CULL_MARGIN, bx1 = (float)(wx0 + 7) + CULL_MARGIN;
+    const float by0 = (float)wy0 - CULL_MARGIN, by1 = (float)(wy0 + 3) + CULL_MARGIN;
 
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
-    const int nb = (n + FWD_BATCH - 1) / FWD_BATCH;
-    const SplatRec* src = recs + range.x;
+    const int nb = (n + RBATCH - 1) / RBATCH;
+    const float4* src = planes + range.x;
 
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
@@ -55,13 +58,8 @@ surfel_render_fwd(const uint2* __restrict__ ranges, const SplatRec* __restrict__
         mbar_fence_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < 2 && b < nb; b++) {
-            uint32_t bytes = (uint32_t)(min(FWD_BATCH, n - b * FWD_BATCH) * sizeof(SplatRec));
-            mbar_expect_tx(&full_bar[b], bytes);
-            bulk_g2s(&sbuf[b][0], src + b * FWD_BATCH, bytes, &full_bar[b]);
-        }
-    }
+    if (threadIdx.x == 0)
+        for (int b = 0; b < 2 && b < nb; b++) issue_batch(sbuf[b], src, pstride, b * RBATCH, min(RBATCH, n - b * RBATCH), &full_bar[b]);
 
     float T = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
@@ -71,66 +69,46 @@ surfel_render_fwd(const uint2* __restrict__ ranges, const SplatRec* __restrict__
     uint32_t last_contrib = 0, med_contrib = 0;
     bool done = !inside;
     bool warp_done = __all_sync(FULLMASK, done);
-    const float MSCALE = FAR_N / (FAR_N - NEAR_N);
 
     for (int b = 0; b < nb; b++) {
         const int stage = b & 1;
         const uint32_t parity = (uint32_t)((b >> 1) & 1);
-        const int cnt = min(FWD_BATCH, n - b * FWD_BATCH);
+        const int cnt = min(RBATCH, n - b * RBATCH);
         if (!warp_done) {
             mbar_wait(&full_bar[stage], parity);
-            const SplatRec* sb = sbuf[stage];
+            const float4(*sb)[RBATCH] = sbuf[stage];
             for (int c0 = 0; c0 < cnt && !warp_done; c0 += 32) {
                 const int e = c0 + lane;
-                uint32_t bits = BOUNDS_EMPTY;
-                if (e < cnt) bits = __float_as_uint(sb[e].cb.w);
-                const int bx0 = bits & 15, bx1 = (bits >> 4) & 15, by0 = (bits >> 8) & 15, by1 = (bits >> 12) & 15;
-                const bool hit = !(bits & BOUNDS_EMPTY) && bx0 <= wx0 + 7 && bx1 >= wx0 && by0 <= wy0 + 3 && by1 >= wy0;
+                bool hit = false;
+                if (e < cnt) hit = entry_hits_block(sb[0][e], sb[1][e], sb[2][e], sb[3][e], bx0, bx1, by0, by1);
                 uint32_t m = __ballot_sync(FULLMASK, hit);
                 while (m) {
                     const int j = c0 + __ffs(m) - 1;
                     m &= m - 1;
-                    const float4* r = reinterpret_cast<const float4*>(sb + j);
-                    const float4 tu = r[0], tv = r[1], tw = r[2];
-                    bool valid = !done;
-                    // ray-splat intersection in tile-local pixel coordinates
-                    const float kx = fmaf(fx, tw.x, -tu.x), ky = fmaf(fx, tw.y, -tu.y), kz = fmaf(fx, tw.z, -tu.z);
-                    const float l0 = fmaf(fy, tw.x, -tv.x), l1 = fmaf(fy, tw.y, -tv.y), l2 = fmaf(fy, tw.z, -tv.z);
-                    const float p0 = ky * l2 - kz * l1, p1 = kz * l0 - kx * l2, p2 = kx * l1 - ky * l0;
-                    valid = valid && (p2 != 0.0f);
-                    const float ip = __frcp_rn(p2);
-                    const float s0 = p0 * ip, s1 = p1 * ip;
-                    const float rho3d = s0 * s0 + s1 * s1;
-                    const float d0 = tu.w - fx, d1 = tv.w - fy;
-                    const float rho2d = FILTER_INV_SQUARE * (d0 * d0 + d1 * d1);
-                    const float rho = fminf(rho3d, rho2d);
-                    const float depth = (rho3d <= rho2d) ? (s0 * tw.x + s1 * tw.y) + tw.z : tw.z;
-                    valid = valid && !(depth < NEAR_N);
-                    const float power = -0.5f * rho;
-                    valid = valid && !(power > 0.0f);
-                    const float alpha = fminf(ALPHA_MAX, tw.w * __expf(power));
-                    valid = valid && !(alpha < ALPHA_MIN);
+                    const float4 qa = sb[0][j], qb = sb[1][j], qc = sb[2][j], qd = sb[3][j];
+                    PairEval ev = eval_pair(qa, qb, qc, qd, fx, fy);
+                    bool valid = ev.valid && !done;
                     if (__any_sync(FULLMASK, valid)) {
-                        const float test_T = T * (1.0f - alpha);
+                        const float test_T = T * (1.0f - ev.alpha);
                         if (valid && test_T < T_EPS) { done = true; valid = false; }
                         if (valid) {
-                            const float4 ng = r[3], cb = r[4];
-                            const float w = alpha * T;
+                            const float4 pn = sb[4][j], pc = sb[5][j];
+                            const float w = ev.alpha * T;
                             const float A = 1.0f - T;
-                            const float mm = MSCALE * (1.0f - NEAR_N * __frcp_rn(depth));
+                            const float mm = MSCALE * (1.0f - NEAR_N * fast_rcp(ev.depth));
                             dist += (mm * mm * A + M2 - 2.0f * mm * M1) * w;
-                            Dacc += depth * w;
+                            Dacc += ev.depth * w;
                             M1 += mm * w;
                             M2 += mm * mm * w;
-                            const uint32_t pos = (uint32_t)(b * FWD_BATCH + j + 1);
+                            const uint32_t pos = (uint32_t)(b * RBATCH + j + 1);
                             if (T > 0.5f) {
-                                med_depth = depth;
-                                surf_idx = (int)__float_as_uint(ng.w);
-                                mn0 = ng.x; mn1 = ng.y; mn2 = ng.z;
+                                med_depth = ev.depth;
+                                surf_idx = (int)(__float_as_uint(qd.w) & ~REC_FLAG_ALWAYS);
+                                mn0 = pn.x; mn1 = pn.y; mn2 = pn.z;
                                 med_contrib = pos;
                             }
-                            N0 += ng.x * w; N1 += ng.y * w; N2 += ng.z * w;
-                            C0 += cb.x * w; C1 += cb.y * w; C2 += cb.z * w;
+                            N0 += pn.x * w; N1 += pn.y * w; N2 += pn.z * w;
+                            C0 += pn.w * w; C1 += pc.x * w; C2 += pc.y * w;
                             T = test_T;
                             last_contrib = pos;
                         }
@@ -147,10 +125,8 @@ surfel_render_fwd(const uint2* __restrict__ ranges, const SplatRec* __restrict__
             break;
         }
         if (threadIdx.x == 0 && b + 2 < nb) {
-            uint32_t bytes = (uint32_t)(min(FWD_BATCH, n - (b + 2) * FWD_BATCH) * sizeof(SplatRec));
             fence_proxy_async();
-            mbar_expect_tx(&full_bar[stage], bytes);
-            bulk_g2s(&sbuf[stage][0], src + (b + 2) * FWD_BATCH, bytes, &full_bar[stage]);
+            issue_batch(sbuf[stage], src, pstride, (b + 2) * RBATCH, min(RBATCH, n - (b + 2) * RBATCH), &full_bar[stage]);
         }
     }
 

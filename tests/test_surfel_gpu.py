@@ -14,8 +14,8 @@ import torch
 import harness as hz
 import synth
 from golden.cases import CASES, build_case
-from test_oracle_golden import (DIST_TOL, FWD_RAW_TOL, FWD_TOL, GRAD_L2_TOL, GRAD_TOL, load,
-                                robust_grad_err)
+from test_oracle_golden import (DIST_TOL, FWD_RAW_TOL, FWD_TOL, GRAD_L2_TOL, GRAD_RAW_L2_TOL, GRAD_TOL,
+                                grad_errors, load)
 
 pytestmark = pytest.mark.gpu
 
@@ -37,9 +37,8 @@ def assert_grads_close(ga, gb, keys):
         if y.size == 0 or ga.get(k) is None:
             continue
         x = np.asarray(ga[k]).reshape(y.shape)
-        assert robust_grad_err(x, y) <= GRAD_TOL, (k, robust_grad_err(x, y))
-        l2 = np.linalg.norm(x.astype(np.float64) - y) / max(np.linalg.norm(y), 1e-30)
-        assert l2 <= GRAD_L2_TOL, (k, l2)
+        linf, l2, raw = grad_errors(x, y)
+        assert linf <= GRAD_TOL and l2 <= GRAD_L2_TOL and raw <= GRAD_RAW_L2_TOL, (k, linf, l2, raw)
 
 
 def grad_keys(kw, sc):
