@@ -12,26 +12,21 @@ namespace gsr {
 // ---- kernels / helpers defined in the other translation units ---------------
 __global__ void surfel_preprocess_fwd(int, int, int, const float*, const float2*, const float4*, const float*,
                                       const float*, const float*, const bool, const ViewParams, const bool,
-                                      const bool, int*, GeomRec*, CullRec*, uint32_t*, float*, uint8_t*, int*);
+                                      const bool, int*, GeomRec*, CullRec*, float*, uint32_t*, uint32_t*, float*, uint8_t*, int*);
 __global__ void surfel_preprocess_bwd(int, int, int, const float*, const float2*, const float4*, const float*,
                                       const bool, const ViewParams, const int, const int, const int*,
                                       const GeomRec*, const uint8_t*, const float*, float*, float*, float*,
                                       float*, float*, float*, float*, float*, float*);
 __global__ void mark_visible_kernel(int, const float*, const ViewParams, uint8_t*);
-__global__ void duplicate_with_keys(int, const GeomRec*, const CullRec*, const int*, const uint32_t*, int, int,
-                                    uint64_t*, uint32_t*);
-__global__ void build_records(int, const uint64_t*, const uint32_t*, const GeomRec*, const CullRec*,
-                              const float*, int, int, int, float4*, size_t, uint2*);
-__global__ void surfel_render_fwd(const uint2*, const float4*, size_t, int, int, int, const float*, float*,
+__global__ void tile_scan(int, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, const int*);
+__global__ void scatter_keys(int, const GeomRec*, const CullRec*, const float*, const int*, const uint32_t*, int, int,
+                             uint32_t*, uint64_t*);
+__global__ void sort_build_records(const uint32_t*, uint64_t*, const GeomRec*, const float*, int, int, int, float4*,
+                                   size_t, int);
+__global__ void surfel_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float*,
                                   uint32_t*, float*, float*);
-__global__ void surfel_render_bwd(const uint2*, const float4*, size_t, int, int, int, const float*,
+__global__ void surfel_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*,
                                   const float*, const uint32_t*, const float*, const float*, float*);
-size_t scan_temp_bytes(int P);
-cudaError_t inclusive_scan(char*, size_t, const uint32_t*, uint32_t*, int, cudaStream_t);
-size_t sort_temp_bytes(int64_t R);
-cudaError_t sort_pairs(char*, size_t, const uint64_t*, uint64_t*, const uint32_t*, uint32_t*, int64_t, int,
-                       cudaStream_t);
-
 // ---- error string -------------------------------------------------------------
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -42,18 +37,16 @@ void set_error(const char* fmt, ...) {
 }
 
 // ---- workspace layouts ----------------------------------------------------------
-size_t GeomWs::carve(GeomWs& w, char* base, int P, size_t scan_bytes) {
+size_t GeomWs::carve(GeomWs& w, char* base, int P) {
     Carver c(base);
     size_t n = P > 0 ? (size_t)P : 1;
     w.geom = c.take<GeomRec>(n);
     w.cull = c.take<CullRec>(n);
-    w.tiles = c.take<uint32_t>(n);
-    w.offsets = c.take<uint32_t>(n);
+    w.depths = c.take<float>(n);
+    w.masks = c.take<uint32_t>(n);
     w.rgb = c.take<float>(3 * n);
     w.clamped = c.take<uint8_t>(3 * n);
     w.flags = c.take<int>(32);
-    w.scan_tmp = c.take<char>(scan_bytes);
-    w.scan_tmp_bytes = scan_bytes;
     return c.used + 256;
 }
 size_t ImageWs::carve(ImageWs& w, char* base, int W, int H) {
@@ -62,32 +55,23 @@ size_t ImageWs::carve(ImageWs& w, char* base, int W, int H) {
     size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
     w.final_T = c.take<float>(3 * N);
     w.n_contrib = c.take<uint32_t>(2 * N);
-    w.ranges = c.take<uint2>(tiles);
+    w.tile_count = c.take<uint32_t>(tiles + 2);
+    w.tile_offset = c.take<uint32_t>(tiles + 1);
+    w.tile_cursor = c.take<uint32_t>(tiles);
     return c.used + 256;
 }
-size_t BinWs::carve(BinWs& w, char* base, int64_t R, int P, size_t sort_bytes) {
+size_t BinWs::carve(BinWs& w, char* base, int64_t R, int P) {
     Carver c(base);
     size_t n = R > 0 ? (size_t)R : 1;
-    w.keys_unsorted = c.take<uint64_t>(n);
     w.keys = c.take<uint64_t>(n);
-    w.vals_unsorted = c.take<uint32_t>(n);
-    w.vals = c.take<uint32_t>(n);
     w.plane_stride = (n + 7) & ~size_t(7);
     w.planes = c.take<float4>(w.plane_stride * REC_PLANES);
     w.gacc = c.take<float>((size_t)(P > 0 ? P : 1) * GACC_STRIDE);
-    w.sort_tmp = c.take<char>(sort_bytes);
-    w.sort_tmp_bytes = sort_bytes;
     return c.used + 256;
 }
 
 static inline char* align256(char* p) {
     return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 255) & ~uintptr_t(255));
-}
-
-static uint32_t ceil_log2_tiles(uint32_t n) {  // bits needed for tile ids 0..n-1 (>= reference's getHigherMsb)
-    uint32_t b = 0;
-    while ((1ull << b) < (unsigned long long)n) b++;
-    return b ? b : 1;
 }
 
 static ViewParams make_view(const float* view, const float* proj, const float* campos, int W, int H,
@@ -101,6 +85,8 @@ static ViewParams make_view(const float* view, const float* proj, const float* c
 }
 
 // ---- runtime options (debug / measurement only; defaults are the product path) ----
+static int g_last_R = 0;      // num_rendered of the previous forward (sizing guess only)
+static int g_dbg = 0;         // developer timing experiments (results invalid when non-zero)
 static int g_no_cull = -1;   // 1: contribution boxes disabled (every pair evaluated, as the reference does)
 static bool no_cull() {
     if (g_no_cull < 0) { const char* e = getenv("GSR_NO_CULL"); g_no_cull = (e && e[0] == '1') ? 1 : 0; }
@@ -153,6 +139,7 @@ const char* gsr_build_arch(void) { return "sm_100a"; }
 int gsr_set_option(const char* name, int value) {
     if (!name) return GSR_E_INVALID;
     if (!strcmp(name, "no_cull")) { g_no_cull = value ? 1 : 0; return GSR_OK; }
+    if (!strcmp(name, "dbg")) { g_dbg = value; return GSR_OK; }
     set_error("gsr_set_option: unknown option %s", name);
     return GSR_E_INVALID;
 }
@@ -207,73 +194,87 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     char* ibase = imageBuffer(user, ibytes);
     if (!ibase) { set_error("imageBuffer callback failed (%zu bytes)", ibytes); return GSR_E_ALLOC; }
     ImageWs::carve(iw, align256(ibase), W, H);
-    GSR_CUDA_CHECK(cudaMemsetAsync(iw.ranges, 0, (size_t)ntiles * sizeof(uint2), s));
+    // tile_count, tile_offset and tile_cursor are adjacent: one memset clears all three
+    GSR_CUDA_CHECK(cudaMemsetAsync(iw.tile_count, 0, (size_t)((char*)(iw.tile_cursor + ntiles) - (char*)iw.tile_count), s));
     ht.mark("imgbuf");
 
     int R = 0;
     GeomWs gw;
     BinWs bw;
     memset(&bw, 0, sizeof(bw));
+    memset(&gw, 0, sizeof(gw));
     if (P > 0) {
-        size_t scan_bytes = scan_temp_bytes(P);
-        size_t gbytes = GeomWs::carve(gw, nullptr, P, scan_bytes);
+        size_t gbytes = GeomWs::carve(gw, nullptr, P);
         char* gbase = geometryBuffer(user, gbytes);
         if (!gbase) { set_error("geometryBuffer callback failed (%zu bytes)", gbytes); return GSR_E_ALLOC; }
-        GeomWs::carve(gw, align256(gbase), P, scan_bytes);
+        GeomWs::carve(gw, align256(gbase), P);
         ht.mark("geombuf");
         GSR_CUDA_CHECK(cudaMemsetAsync(gw.flags, 0, 32 * sizeof(int), s));
 
         prof_begin(GSR_PROF_PREPROCESS_FWD, s);
         surfel_preprocess_fwd<<<(P + 255) / 256, 256, 0, s>>>(
             P, D, M, means3D, (const float2*)scales, (const float4*)rotations, opacities, shs, transMat_precomp,
-            colors_precomp != nullptr, vc, prefiltered != 0, no_cull(), radii, gw.geom, gw.cull, gw.tiles,
-            gw.rgb, gw.clamped, gw.flags);
+            colors_precomp != nullptr, vc, prefiltered != 0, no_cull(), radii, gw.geom, gw.cull, gw.depths, gw.masks,
+            iw.tile_count, gw.rgb, gw.clamped, gw.flags);
         prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         prof_begin(GSR_PROF_SCAN, s);
-        GSR_CUDA_CHECK(inclusive_scan(gw.scan_tmp, gw.scan_tmp_bytes, gw.tiles, gw.offsets, P, s));
+        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.tile_count + ntiles,
+                                     gw.flags);
         prof_end(GSR_PROF_SCAN, s);
-        // num_rendered sizes the binning buffer: same single read-back as the reference
-        // (S/rasterizer_impl.cu:282), plus the prefiltered flag.
-        uint32_t Ru = 0;
-        int flag = 0;
+        GSR_CUDA_CHECK(cudaGetLastError());
         ht.mark("launch_pre");
-        GSR_CUDA_CHECK(cudaMemcpyAsync(&Ru, gw.offsets + (P - 1), 4, cudaMemcpyDeviceToHost, s));
-        GSR_CUDA_CHECK(cudaMemcpyAsync(&flag, gw.flags, 4, cudaMemcpyDeviceToHost, s));
+        // Speculative binning buffer: ask for last call's R (+25%) BEFORE blocking on the read-back, so
+        // that in steady state nothing but three kernel launches stands between the read-back and
+        // the GPU resuming.  A second, exact request follows only when the guess was too small.
+        const int R_guess = g_last_R > 0 ? (int)fmin(2.0e9, 1.25 * (double)g_last_R + 4096.0) : 0;
+        char* bbase = nullptr;
+        size_t bcap = 0;
+        if (R_guess > 0) {
+            bcap = BinWs::carve(bw, nullptr, R_guess, P);
+            bbase = binningBuffer(user, bcap);
+            if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bcap); return GSR_E_ALLOC; }
+        }
+        ht.mark("binbuf_spec");
+        // num_rendered sizes the binning buffer: the same single read-back as the reference
+        // (S/rasterizer_impl.cu:282); the prefiltered flag rides along.
+        uint32_t rb[2] = {0u, 0u};
+        GSR_CUDA_CHECK(cudaMemcpyAsync(rb, iw.tile_count + ntiles, 8, cudaMemcpyDeviceToHost, s));
         GSR_CUDA_CHECK(cudaStreamSynchronize(s));
-        if (flag) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
-        if (Ru > 0x7fffff00u) { set_error("num_rendered overflow (%u)", Ru); return GSR_E_OVERFLOW; }
-        R = (int)Ru;
+        if (rb[1]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
+        if (rb[0] > 0x7fffff00u) { set_error("num_rendered overflow (%u)", rb[0]); return GSR_E_OVERFLOW; }
+        R = (int)rb[0];
+        g_last_R = R;
         ht.mark("sync_R");
+        size_t bbytes = BinWs::carve(bw, nullptr, R, P);
+        if (!bbase || bbytes > bcap) {
+            bbase = binningBuffer(user, bbytes);
+            if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
+        }
+        BinWs::carve(bw, align256(bbase), R, P);
+        ht.mark("binbuf");
+    } else {
+        size_t bbytes = BinWs::carve(bw, nullptr, 0, 0);
+        char* bbase = binningBuffer(user, bbytes);
+        if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
+        BinWs::carve(bw, align256(bbase), 0, 0);
     }
-
-    size_t sort_bytes = R > 0 ? sort_temp_bytes(R) : 0;
-    size_t bbytes = BinWs::carve(bw, nullptr, R, P, sort_bytes);
-    char* bbase = binningBuffer(user, bbytes);
-    if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
-    BinWs::carve(bw, align256(bbase), R, P, sort_bytes);
-    ht.mark("binbuf");
 
     if (R > 0) {
         prof_begin(GSR_PROF_DUPLICATE, s);
-        duplicate_with_keys<<<(P + 255) / 256, 256, 0, s>>>(P, gw.geom, gw.cull, radii, gw.offsets, vc.gx, vc.gy,
-                                                            bw.keys_unsorted, bw.vals_unsorted);
+        scatter_keys<<<(P + 255) / 256, 256, 0, s>>>(P, gw.geom, gw.cull, gw.depths, radii, gw.masks, vc.gx, vc.gy,
+                                                     iw.tile_cursor, bw.keys);
         prof_end(GSR_PROF_DUPLICATE, s);
         GSR_CUDA_CHECK(cudaGetLastError());
-        int end_bit = 32 + (int)ceil_log2_tiles((uint32_t)ntiles);
-        prof_begin(GSR_PROF_SORT, s);
-        GSR_CUDA_CHECK(sort_pairs(bw.sort_tmp, bw.sort_tmp_bytes, bw.keys_unsorted, bw.keys, bw.vals_unsorted,
-                                  bw.vals, R, end_bit, s));
-        prof_end(GSR_PROF_SORT, s);
         const float* colors = colors_precomp ? colors_precomp : gw.rgb;
         prof_begin(GSR_PROF_BUILD_RECORDS, s);
-        build_records<<<(R + 255) / 256, 256, 0, s>>>(R, bw.keys, bw.vals, gw.geom, gw.cull, colors, vc.gx, W, H,
-                                                      bw.planes, bw.plane_stride, iw.ranges);
+        sort_build_records<<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, vc.gx, W, H,
+                                                  bw.planes, bw.plane_stride, g_dbg);
         prof_end(GSR_PROF_BUILD_RECORDS, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }
     prof_begin(GSR_PROF_RENDER_FWD, s);
-    surfel_render_fwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.planes, bw.plane_stride, W, H, vc.gx, background,
+    surfel_render_fwd<<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
                                                   iw.final_T, iw.n_contrib, out_color, out_others);
     prof_end(GSR_PROF_RENDER_FWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
@@ -308,14 +309,14 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
     const int ntiles = vc.gx * vc.gy;
 
     GeomWs gw; ImageWs iw; BinWs bw;
-    GeomWs::carve(gw, align256(geom_buffer), P, scan_temp_bytes(P));
+    GeomWs::carve(gw, align256(geom_buffer), P);
     ImageWs::carve(iw, align256(image_buffer), W, H);
-    BinWs::carve(bw, align256(binning_buffer), R, P, R > 0 ? sort_temp_bytes(R) : 0);
+    BinWs::carve(bw, align256(binning_buffer), R, P);
 
     GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * GACC_STRIDE * sizeof(float), s));
     if (R > 0) {
         prof_begin(GSR_PROF_RENDER_BWD, s);
-        surfel_render_bwd<<<ntiles, TILE_PIX, 0, s>>>(iw.ranges, bw.planes, bw.plane_stride, W, H, vc.gx, background,
+        surfel_render_bwd<<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
                                                       iw.final_T, iw.n_contrib, dL_dpix, dL_dothers,
                                                       bw.gacc);
         prof_end(GSR_PROF_RENDER_BWD, s);

@@ -1,107 +1,186 @@
-// binning.cu -- tile binning for sm_100a: (tile | depth) key emission, device radix sort,
-// and materialisation of the sorted per-(Gaussian, tile) record planes with per-tile ranges.
+// binning.cu -- tile binning for sm_100a without a global sort.
 //
 // Ordering contract (identical to the reference, S/cuda_rasterizer/rasterizer_impl.cu:70-138,
-// 301-315): key = tile_id << 32 | float_bits(view depth); stable LSD radix sort over
-// bits [0, 32 + ceil_log2(tiles)), so ties keep ascending Gaussian index.
-// Difference: a (Gaussian, tile) pair of the reference's getRect rectangle is only emitted
-// when the splat can reach alpha >= 1/255 somewhere in that tile (cull.cuh); the dropped
-// pairs are exactly list entries on which every pixel of the tile would `continue`.
+// 301-315): within a tile, entries are ordered by (float bits of view depth, Gaussian index) --
+// exactly what the reference's stable radix sort of (tile << 32 | depth_bits) keys over pairs
+// emitted in ascending Gaussian index produces.  The reference sorts all R pairs globally
+// (6 radix passes over 12-byte pairs); here the tile is known when a pair is emitted, so
+//   1. the forward preprocess counts pairs per tile (atomicAdd on a tiles-sized histogram),
+//   2. tile_scan turns counts into per-tile offsets (one CTA; also yields R),
+//   3. scatter_keys drops each pair's 64-bit (depth_bits << 32 | index) key into its tile's
+//      bucket (slot order inside a bucket is arbitrary -- the key is a total order),
+//   4. sort_build_records: one CTA per tile sorts its bucket with a bitonic network in shared
+//      memory (global memory for oversized buckets) and, fused, materialises the tile-local
+//      record planes the render kernels stream (six float4 planes, coalesced stores).
+// A (Gaussian, tile) pair of the reference's getRect rectangle is only emitted when the splat
+// can reach alpha >= 1/255 somewhere in that tile (cull.cuh); dropped pairs are list entries
+// on which every pixel of the tile would `continue`.
 #include "common.cuh"
 #include "cull.cuh"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 namespace gsr {
 
-size_t scan_temp_bytes(int P) {
-    size_t n = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, n, (uint32_t*)nullptr, (uint32_t*)nullptr, P);
-    return n;
+// ---- 2. exclusive scan of per-tile counts (single CTA) -------------------------------------
+__global__ void __launch_bounds__(1024)
+tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+          uint32_t* __restrict__ cursors, uint32_t* __restrict__ total, const int* __restrict__ flags) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < ntiles ? counts[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane], s = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sums[lane] = s - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sums[warp] + (x - v);
+        if (i < ntiles) { offsets[i] = excl; cursors[i] = excl; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    // total[0] = R, total[1] = prefiltered-violation flag: one 8-byte read-back for the host
+    if (threadIdx.x == 0) { offsets[ntiles] = carry; total[0] = carry; total[1] = (uint32_t)flags[0]; }
 }
 
-cudaError_t inclusive_scan(char* tmp, size_t tmp_bytes, const uint32_t* in, uint32_t* out, int P,
-                           cudaStream_t s) {
-    return cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, in, out, P, s);
-}
-
-size_t sort_temp_bytes(int64_t R) {
-    size_t n = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, n, (uint64_t*)nullptr, (uint64_t*)nullptr,
-                                    (uint32_t*)nullptr, (uint32_t*)nullptr, (int)R);
-    return n;
-}
-
-cudaError_t sort_pairs(char* tmp, size_t tmp_bytes, const uint64_t* kin, uint64_t* kout,
-                       const uint32_t* vin, uint32_t* vout, int64_t R, int end_bit, cudaStream_t s) {
-    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, (int)R, 0, end_bit, s);
-}
-
-// One thread per Gaussian; writes its (key, index) pairs at its scan offset.
+// ---- 3. scatter (depth, index) keys into tile buckets ---------------------------------------
 __global__ void __launch_bounds__(256)
-duplicate_with_keys(int P, const GeomRec* __restrict__ geom, const CullRec* __restrict__ cull,
-                    const int* __restrict__ radii, const uint32_t* __restrict__ offsets, int gx, int gy,
-                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+scatter_keys(int P, const GeomRec* __restrict__ geom, const CullRec* __restrict__ cull,
+             const float* __restrict__ depths, const int* __restrict__ radii, const uint32_t* __restrict__ masks, int gx, int gy,
+             uint32_t* __restrict__ cursors, uint64_t* __restrict__ keys) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
-    int r = radii[idx];
+    const int r = radii[idx];
     if (r <= 0) return;
-    uint32_t off = idx == 0 ? 0u : offsets[idx - 1];
-    const uint32_t end = offsets[idx];
-    if (off == end) return;
+    const uint32_t mask = masks[idx];
+    if (mask == 0u) return;
     const float cx = geom[idx].tu.w, cy = geom[idx].tv.w;
-    const uint32_t dbits = __float_as_uint(geom[idx].nd.w);
-    const CullRec cr = cull[idx];
+    const uint64_t key = ((uint64_t)__float_as_uint(depths[idx]) << 32) | (uint32_t)idx;
     int x0, y0, x1, y1;
     get_rect(cx, cy, r, gx, gy, x0, y0, x1, y1);
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            if (!tile_may_contribute(cr, cx, cy, x, y)) continue;
-            if (off >= end) return;  // cannot happen (same test as the count); never write past the slot range
-            keys[off] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
-            vals[off] = (uint32_t)idx;
-            off++;
+    if (mask != MASK_RETEST) {
+        // the preprocess recorded which tiles of the (<= 32 tile) rect passed the test
+        const int w = x1 - x0;
+        uint32_t m = mask;
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const int tile = (y0 + k / w) * gx + (x0 + k % w);
+            keys[atomicAdd(&cursors[tile], 1u)] = key;
         }
+    } else {
+        const CullRec cr = cull[idx];
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++)
+                if (tile_may_contribute(cr, cx, cy, x, y)) keys[atomicAdd(&cursors[y * gx + x], 1u)] = key;
+    }
 }
 
-// One thread per sorted list entry: builds the tile-local record (six float4 planes, coalesced
-// stores) and marks tile range boundaries (identifyTileRanges, S/rasterizer_impl.cu:116-138).
-__global__ void __launch_bounds__(256)
-build_records(int R, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-              const GeomRec* __restrict__ geom, const CullRec* __restrict__ cull,
-              const float* __restrict__ colors, int gx, int W, int H, float4* __restrict__ planes, size_t pstride,
-              uint2* __restrict__ ranges) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t tile = (uint32_t)(keys[i] >> 32);
-    if (i == 0) ranges[tile].x = 0;
-    else {
-        uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
-        if (prev != tile) { ranges[prev].y = i; ranges[tile].x = i; }
-    }
-    if (i == R - 1) ranges[tile].y = R;
+// ---- 4. per-tile sort fused with record materialisation --------------------------------------
+constexpr int SORT_SMEM_CAP = 4096;            // keys sorted in shared memory (32 KB)
+constexpr uint64_t KEY_INF = ~0ull;
 
-    const uint32_t g = vals[i];
-    const float4* gp = reinterpret_cast<const float4*>(geom + g);
-    const float4 tu = __ldg(gp), tv = __ldg(gp + 1), tw = __ldg(gp + 2), nd = __ldg(gp + 3);
-    const float4 c1 = __ldg(&cull[g].q1), c2 = __ldg(&cull[g].q2);
+// All-ascending bitonic network on m = pow2 >= n virtual slots; slots >= n hold +inf and are
+// never materialised when sorting in global memory (a compare against them is a no-op).
+template <bool kShared>
+__device__ __forceinline__ void bitonic_sort(uint64_t* __restrict__ k, int n, int m) {
+    for (int lsize = 1; (1 << lsize) <= m; lsize++) {
+        const int size = 1 << lsize;
+        for (int ls = lsize - 1; ls >= 0; ls--) {
+            const int stride = 1 << ls;
+            const bool first = (ls == lsize - 1);
+            // comparators are handled two at a time per thread (all four loads first: ILP)
+            for (int t0 = threadIdx.x; t0 < (m >> 1); t0 += 2 * blockDim.x) {
+                const int t1 = t0 + blockDim.x;
+                // t-th comparator of this step: lower index lo, partner hi > lo
+                const int lo0 = ((t0 >> ls) << (ls + 1)) | (t0 & (stride - 1));
+                const int hi0 = first ? (lo0 ^ (size - 1)) : (lo0 | stride);
+                const int lo1 = ((t1 >> ls) << (ls + 1)) | (t1 & (stride - 1));
+                const int hi1 = first ? (lo1 ^ (size - 1)) : (lo1 | stride);
+                const bool ok0 = kShared || hi0 < n, ok1 = (t1 < (m >> 1)) && (kShared || hi1 < n);
+                uint64_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+                if (ok0) { a0 = k[lo0]; b0 = k[hi0]; }
+                if (ok1) { a1 = k[lo1]; b1 = k[hi1]; }
+                if (ok0 && a0 > b0) { k[lo0] = b0; k[hi0] = a0; }
+                if (ok1 && a1 > b1) { k[lo1] = b1; k[hi1] = a1; }
+            }
+            // comparators t = 32w .. 32w+31 of a step with stride <= 32 only touch the 64-slot
+            // window [64w, 64w+64): a warp-level sync suffices when this step wrote and the next
+            // step reads inside that window
+            const int next_stride = ls > 0 ? (stride >> 1) : size;
+            if (kShared && stride <= 32 && next_stride <= 32) __syncwarp();
+            else __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sort_build_records(const uint32_t* __restrict__ offsets, uint64_t* __restrict__ keys,
+                   const GeomRec* __restrict__ geom,
+                   const float* __restrict__ colors, int gx, int W, int H, float4* __restrict__ planes,
+                   size_t pstride, int dbg) {
+    __shared__ uint64_t skeys[SORT_SMEM_CAP];
+    const int tile = blockIdx.x;
+    const uint32_t begin = offsets[tile], end = offsets[tile + 1];
+    const int n = (int)(end - begin);
+    if (n == 0) return;
+    uint64_t* gk = keys + begin;
+    int m = 1;
+    while (m < n) m <<= 1;
+    const uint64_t* sorted;
+    if (m <= SORT_SMEM_CAP) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) skeys[i] = i < n ? gk[i] : KEY_INF;
+        __syncthreads();
+        if (n > 1 && !(dbg & 1)) bitonic_sort<true>(skeys, n, m);
+        sorted = skeys;
+    } else {
+        bitonic_sort<false>(gk, n, m);
+        sorted = gk;
+    }
     const float ox = (float)((tile % gx) * TILE), oy = (float)((tile / gx) * TILE);
-    const float3 Tw = make_float3(tw.x, tw.y, tw.z);
-    const float3 Tu = make_float3(fmaf(-ox, tw.x, tu.x), fmaf(-ox, tw.y, tu.y), fmaf(-ox, tw.z, tu.z));
-    const float3 Tv = make_float3(fmaf(-oy, tw.x, tv.x), fmaf(-oy, tw.y, tv.y), fmaf(-oy, tw.z, tv.z));
-    const float3 a = cross3(Tv, Tw), b = cross3(Tw, Tu), c = cross3(Tu, Tv);
-    const float det = dot3(c, Tw);
-    const uint32_t flag = ((int)c2.z == CULL_EXACT) ? 0u : REC_FLAG_ALWAYS;
-    planes[0 * pstride + i] = make_float4(a.x, a.y, a.z, tu.w - ox);
-    planes[1 * pstride + i] = make_float4(b.x, b.y, b.z, tv.w - oy);
-    planes[2 * pstride + i] = make_float4(c.x, c.y, c.z, tw.w);
-    planes[3 * pstride + i] = make_float4(det, c1.w, tw.z, __uint_as_float(g | flag));
-    const float cr = __ldg(colors + 3 * (size_t)g), cg = __ldg(colors + 3 * (size_t)g + 1),
-                cb = __ldg(colors + 3 * (size_t)g + 2);
-    planes[4 * pstride + i] = make_float4(nd.x, nd.y, nd.z, cr);
-    // moment frame of the backward: the splat's rounded, image-clamped screen centre (tile-local)
-    const float sx = moment_origin(tu.w, W), sy = moment_origin(tv.w, H);
-    planes[5 * pstride + i] = make_float4(cg, cb, sx - ox, sy - oy);
+    if (dbg & 2) return;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t g = (uint32_t)(sorted[i] & 0xffffffffull);
+        const float4* gp = reinterpret_cast<const float4*>(geom + g);
+        const float4 tu = __ldg(gp), tv = __ldg(gp + 1), tw = __ldg(gp + 2), nd = __ldg(gp + 3);
+        const float cr = __ldg(colors + 3 * (size_t)g), cg = __ldg(colors + 3 * (size_t)g + 1),
+                    cb = __ldg(colors + 3 * (size_t)g + 2);
+        const float3 Tw = make_float3(tw.x, tw.y, tw.z);
+        const float3 Tu = make_float3(fmaf(-ox, tw.x, tu.x), fmaf(-ox, tw.y, tu.y), fmaf(-ox, tw.z, tu.z));
+        const float3 Tv = make_float3(fmaf(-oy, tw.x, tv.x), fmaf(-oy, tw.y, tv.y), fmaf(-oy, tw.z, tv.z));
+        const float3 a = cross3(Tv, Tw), b = cross3(Tw, Tu), c = cross3(Tu, Tv);
+        const float det = dot3(c, Tw);
+        // nd.w = tau (>= 0: conic is an ellipse) or -(tau + 1) (always evaluate)
+        const bool always = nd.w < 0.f;
+        const float tau = always ? -nd.w - 1.f : nd.w;
+        const uint32_t flag = always ? REC_FLAG_ALWAYS : 0u;
+        const size_t o = (size_t)begin + i;
+        planes[0 * pstride + o] = make_float4(a.x, a.y, a.z, tu.w - ox);
+        planes[1 * pstride + o] = make_float4(b.x, b.y, b.z, tv.w - oy);
+        planes[2 * pstride + o] = make_float4(c.x, c.y, c.z, tw.w);
+        planes[3 * pstride + o] = make_float4(det, tau, tw.z, __uint_as_float(g | flag));
+        planes[4 * pstride + o] = make_float4(nd.x, nd.y, nd.z, cr);
+        // moment frame of the backward: the splat's rounded, image-clamped screen centre (tile-local)
+        const float sx = moment_origin(tu.w, W), sy = moment_origin(tv.w, H);
+        planes[5 * pstride + o] = make_float4(cg, cb, sx - ox, sy - oy);
+    }
 }
 
 }  // namespace gsr

@@ -42,7 +42,7 @@ struct __align__(16) GeomRec {
     float4 tu;  // Tu.xyz (x*w row of the splat->pixel homography), aabb centre x
     float4 tv;  // Tv.xyz,                                          aabb centre y
     float4 tw;  // Tw.xyz,                                          opacity
-    float4 nd;  // view-space normal (facing the camera),           view depth
+    float4 nd;  // view-space normal (facing the camera),           tau (>= 0) or -(tau+1): "always evaluate"
 };
 
 // Per-Gaussian culling record (forward preprocess -> tile binning / record build).
@@ -88,37 +88,34 @@ struct Carver {
     }
 };
 
+constexpr uint32_t MASK_RETEST = 0xffffffffu;   // rect larger than 32 tiles: scatter re-runs the tile test
+
 struct GeomWs {      // geometryBuffer
     GeomRec* geom;       // P
     CullRec* cull;       // P
-    uint32_t* tiles;     // P  tiles touched
-    uint32_t* offsets;   // P  inclusive scan
+    float* depths;       // P  view depth (sort key bits)
+    uint32_t* masks;     // P  bit k set: k-th tile (row-major) of the getRect rectangle is reachable
     float* rgb;          // 3P (SH path only; else unused)
     uint8_t* clamped;    // 3P
     int* flags;          // [0] prefiltered violation, [1..] reserved
-    char* scan_tmp;
-    size_t scan_tmp_bytes;
-    static size_t carve(GeomWs& w, char* base, int P, size_t scan_tmp_bytes);
+    static size_t carve(GeomWs& w, char* base, int P);
 };
 
 struct ImageWs {     // imageBuffer
     float* final_T;      // 3N: T, M1, M2   (S/cuda_rasterizer/forward.cu:429-437)
     uint32_t* n_contrib; // 2N: last contributor, median contributor
-    uint2* ranges;       // tiles
+    uint32_t* tile_count;   // tiles (+1: [tiles] = total R written by tile_scan)
+    uint32_t* tile_offset;  // tiles + 1: tile t owns list entries [offset[t], offset[t+1])
+    uint32_t* tile_cursor;  // tiles: scatter cursors
     static size_t carve(ImageWs& w, char* base, int W, int H);
 };
 
 struct BinWs {       // binningBuffer
-    uint64_t* keys_unsorted;
-    uint64_t* keys;
-    uint32_t* vals_unsorted;
-    uint32_t* vals;
+    uint64_t* keys;      // R  (depth_bits << 32 | index), bucketed by tile
     float4* planes;      // REC_PLANES x Rpad float4 (plane stride = Rpad)
     size_t plane_stride; // Rpad = R rounded up to a multiple of 8 (keeps every plane 128-byte aligned)
     float* gacc;         // P * GACC_STRIDE (backward accumulators; lives here so forward owns one blob)
-    char* sort_tmp;
-    size_t sort_tmp_bytes;
-    static size_t carve(BinWs& w, char* base, int64_t R, int P, size_t sort_tmp_bytes);
+    static size_t carve(BinWs& w, char* base, int64_t R, int P);
 };
 
 // Per-view constants.  view/proj/campos stay DEVICE pointers exactly as the reference

@@ -82,13 +82,13 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
                       const float* __restrict__ opacities, const float* __restrict__ shs,
                       const float* __restrict__ transMat_precomp, const bool has_colors,
                       const ViewParams vc, const bool prefiltered, const bool no_cull,
-                      int* __restrict__ radii, GeomRec* __restrict__ geom, CullRec* __restrict__ cull,
-                      uint32_t* __restrict__ tiles, float* __restrict__ rgb,
+                      int* __restrict__ radii, GeomRec* __restrict__ geom, CullRec* __restrict__ cull, float* __restrict__ depths,
+                      uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_count, float* __restrict__ rgb,
                       uint8_t* __restrict__ clamped, int* __restrict__ flags) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     int radius_out = 0;
-    uint32_t tiles_out = 0;
+    uint32_t mask_out = 0;
     float view[16];
     load16(vc.view, view);
     do {
@@ -162,19 +162,27 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
         g.tu = make_float4(Tu.x, Tu.y, Tu.z, cx);
         g.tv = make_float4(Tv.x, Tv.y, Tv.z, cy);
         g.tw = make_float4(Tw.x, Tw.y, Tw.z, opa);
-        g.nd = make_float4(normal.x, normal.y, normal.z, pv.z);
-        geom[idx] = g;
         const CullRec cr = make_cull_rec(Tu, Tv, Tw, cx, cy, opa, no_cull);
         cull[idx] = cr;
+        g.nd = make_float4(normal.x, normal.y, normal.z, ((int)cr.q2.z == CULL_EXACT) ? cr.q1.w : -(cr.q1.w + 1.f));
+        geom[idx] = g;
+        depths[idx] = pv.z;
         radius_out = ri;
-        // tiles of the reference rect (S/auxiliary.h:69-79) that the splat can actually reach
-        uint32_t n = 0;
+        // tiles of the reference rect (S/auxiliary.h:69-79) that the splat can actually reach:
+        // count them per tile (bucket sizes) and remember which ones as a bit mask
+        const int w = x1 - x0, area = w * (y1 - y0);
+        uint32_t m = 0;
+        int k = 0;
         for (int ty = y0; ty < y1; ty++)
-            for (int tx = x0; tx < x1; tx++) n += tile_may_contribute(cr, cx, cy, tx, ty) ? 1u : 0u;
-        tiles_out = n;
+            for (int tx = x0; tx < x1; tx++, k++)
+                if (tile_may_contribute(cr, cx, cy, tx, ty)) {
+                    atomicAdd(&tile_count[ty * vc.gx + tx], 1u);
+                    if (k < 32) m |= 1u << k;
+                }
+        mask_out = area <= 32 ? m : MASK_RETEST;
     } while (0);
     radii[idx] = radius_out;
-    tiles[idx] = tiles_out;
+    masks[idx] = mask_out;
 }
 
 // quat_to_rotmat_vjp, S/auxiliary.h:240-284. vR columns c0,c1,c2 (column-major).

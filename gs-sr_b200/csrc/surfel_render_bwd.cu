@@ -71,8 +71,8 @@ __device__ __forceinline__ float warp_sum(float x) {
     return x;
 }
 
-__global__ void __launch_bounds__(TILE_PIX)
-surfel_render_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ planes, size_t pstride, int W,
+__global__ void __launch_bounds__(TILE_PIX, 3)
+surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, const float* __restrict__ final_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
                   const float* __restrict__ dL_dothers, float* __restrict__ gacc) {
@@ -93,9 +93,9 @@ surfel_render_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ p
     const size_t N = (size_t)W * H;
     const size_t pid = (size_t)py * W + px;
 
-    const uint2 range = ranges[tile];
-    const int n = (int)(range.y - range.x);
-    const float4* src = planes + range.x;
+    const uint32_t range_x = tile_offset[tile];
+    const int n = (int)(tile_offset[tile + 1] - range_x);
+    const float4* src = planes + range_x;
 
     const int last = inside ? (int)n_contrib[pid] : 0;  // entries [0, last) contribute
     const int medpos = inside ? (int)n_contrib[pid + N] - 1 : -1;

@@ -28,7 +28,7 @@
 namespace gsr {
 
 __global__ void __launch_bounds__(TILE_PIX)
-surfel_render_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ planes, size_t pstride, int W,
+surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, float* __restrict__ final_T,
                   uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                   float* __restrict__ out_others) {
@@ -47,10 +47,10 @@ surfel_render_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ p
     const float bx0 = (float)wx0 - CULL_MARGIN, bx1 = (float)(wx0 + 7) + CULL_MARGIN;
     const float by0 = (float)wy0 - CULL_MARGIN, by1 = (float)(wy0 + 3) + CULL_MARGIN;
 
-    const uint2 range = ranges[tile];
-    const int n = (int)(range.y - range.x);
+    const uint32_t range_x = tile_offset[tile];
+    const int n = (int)(tile_offset[tile + 1] - range_x);
     const int nb = (n + RBATCH - 1) / RBATCH;
-    const float4* src = planes + range.x;
+    const float4* src = planes + range_x;
 
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);

@@ -64,6 +64,22 @@ def last_num_rendered():
     return _LAST["num_rendered"]
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _on_device(device):
+    """Device guard only when the tensors live on a non-current device."""
+    return _NULL if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+
 def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -100,14 +116,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         others = torch.empty((11, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         bufs = TorchBuffers(dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev), bufs:
             if P == 0:
                 # reference returns zero-filled outputs without launching (S/rasterize_points.cu:99-100)
                 color.zero_(); others.zero_()
                 num_rendered = 0
             else:
                 num_rendered = check(lib().gsr_surfel_forward(
-                    bufs.geom_fn, bufs.binning_fn, bufs.image_fn, None, P, int(rs.sh_degree), M, ptr(bg), W, H,
+                    bufs.geom_fn, bufs.binning_fn, bufs.image_fn, bufs.user, P, int(rs.sh_degree), M, ptr(bg), W, H,
                     ptr(means3D_c), ptr(sh_c), ptr(colors_c), ptr(opac_c), ptr(scales_c),
                     float(rs.scale_modifier), ptr(rot_c), ptr(tm_c), ptr(view), ptr(proj), ptr(campos),
                     float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)), ptr(color), ptr(others),
@@ -148,7 +164,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_scales, grad_rot = torch.zeros((P, 2), dtype=torch.float32, device=dev), \
             torch.zeros((P, 4), dtype=torch.float32, device=dev)
         if P != 0:
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 check(lib().gsr_surfel_backward(
                     P, int(rs.sh_degree), M, int(ctx.num_rendered), ptr(bg), W, H, ptr(means3D_c), ptr(sh_c),
                     ptr(colors_c), ptr(scales_c), float(rs.scale_modifier), ptr(rot_c), ptr(tm_c), ptr(view),
@@ -183,7 +199,7 @@ class GaussianRasterizer(nn.Module):
             pos = _f32c(positions, "positions", dev)
             present = torch.zeros((P,), dtype=torch.bool, device=dev)
             if P:
-                with torch.cuda.device(dev):
+                with _on_device(dev):
                     check(lib().gsr_mark_visible(P, ptr(pos), ptr(_f32c(rs.viewmatrix, "viewmatrix", dev)),
                                                  ptr(_f32c(rs.projmatrix, "projmatrix", dev)),
                                                  present.data_ptr(), _stream_ptr(dev)), "gsr_mark_visible")

@@ -59,29 +59,50 @@ def ptr(t):
     return t.data_ptr()
 
 
+# The three resize callbacks of the reference protocol (S/rasterize_points.cu:31-37) are created
+# ONCE per process (building a ctypes thunk costs more than the allocation it performs); the
+# `user` pointer carries the id of the TorchBuffers instance that serves the call.
+_ACTIVE = {}
+_NEXT_ID = [1]
+
+
+def _make_cb(name):
+    def cb(user, nbytes):
+        try:
+            return _ACTIVE[user].alloc(name, int(nbytes))
+        except Exception:  # surfaced as GSR_E_ALLOC by the library
+            return 0
+    return BUFFER_FN(cb)
+
+
+GEOM_FN, BINNING_FN, IMAGE_FN = _make_cb("geom"), _make_cb("binning"), _make_cb("image")
+
+
 class TorchBuffers:
-    """The three resize callbacks of the reference protocol (S/rasterize_points.cu:31-37),
-    backed by torch's caching allocator on the tensors' device."""
+    """Scratch owner for one forward call, backed by torch's caching allocator on `device`."""
+
+    geom_fn, binning_fn, image_fn = GEOM_FN, BINNING_FN, IMAGE_FN
 
     def __init__(self, device):
         import torch
+        self._torch = torch
         self.device = device
         self.tensors = {}
-        self._torch = torch
+        self.user = _NEXT_ID[0]
+        _NEXT_ID[0] += 1
 
-        def make(name):
-            def cb(_user, nbytes):
-                try:
-                    t = self._torch.empty(int(nbytes) + 256, dtype=self._torch.uint8, device=self.device)
-                    self.tensors[name] = t
-                    return t.data_ptr()
-                except Exception:  # pragma: no cover - surfaced as GSR_E_ALLOC
-                    return 0
-            return BUFFER_FN(cb)
+    def __enter__(self):
+        _ACTIVE[self.user] = self
+        return self
 
-        self.geom_fn = make("geom")
-        self.binning_fn = make("binning")
-        self.image_fn = make("image")
+    def __exit__(self, *exc):
+        _ACTIVE.pop(self.user, None)
+        return False
+
+    def alloc(self, name, nbytes):
+        t = self._torch.empty(nbytes + 256, dtype=self._torch.uint8, device=self.device)
+        self.tensors[name] = t
+        return t.data_ptr()
 
     def get(self, name):
         t = self.tensors.get(name)
