@@ -41,7 +41,7 @@ P_DEFAULT, W_DEFAULT, H_DEFAULT = 2_000_000, 1600, 1060
 METRIC = "rasterizer fwd+bwd Gaussians/s @ 2M surfels x 1600x1060"
 PROF_NAMES = ["preprocess_fwd", "scan", "duplicate", "sort", "build_records", "render_fwd", "render_bwd",
               "preprocess_bwd"]
-OWN_KERNELS_PER_STEP = 6  # preprocess_fwd, duplicate_with_keys, build_records, render_fwd, render_bwd, preprocess_bwd
+OWN_KERNELS_PER_STEP = 7  # preprocess_fwd, tile_scan, scatter_keys, sort_build_records, render_fwd, render_bwd, preprocess_bwd
 
 
 class ClockSampler:
@@ -107,11 +107,61 @@ def algorithmic_bytes(P, V, R, N):
     """SURVEY 8(d) per-unit figures restated for this repo's layouts (DESIGN.md 'Measurement')."""
     return {
         "preprocess_fwd": P * 40 + V * (64 + 16) + P * 8,
-        "render_fwd": R * 80 + N * 76,
-        "render_bwd": R * 80 + N * 76 + V * 80,
+        "render_fwd": R * 96 + N * 76,
+        "render_bwd": R * 96 + N * 76 + V * 80,
         "whole_step": P * (40 + 24 + 112) + V * (64 + 12 + 76 + 148 + 44) + R * (12 + 24 * 6 + 8 + 80 + 80)
         + N * (76 + 76),
     }
+
+
+def pipelined_e2e(step_fn, host, template, out_host, steps, barrier):
+    """End-to-end loop: every step's inputs travel host(pinned)->device and its rendered image
+    device->host(pinned) INSIDE the timed region.  Copies run on side streams, double buffered,
+    so step i+1's H2D and step i-1's D2H overlap step i's kernels (what a prefetching data
+    loader does); the first H2D and the last D2H are exposed and counted.  Returns milliseconds."""
+    import torch
+    cur = torch.cuda.current_stream()
+    h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    staged = [{k: torch.empty_like(v) for k, v in template.items()} for _ in range(2)]
+    outs = [torch.empty(out_host.shape, dtype=out_host.dtype, device=cur.device) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    rendered = [torch.cuda.Event() for _ in range(2)]
+    fetched = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        b = i & 1
+        with torch.cuda.stream(h2d):
+            if i >= 2:
+                h2d.wait_event(consumed[b])
+            for k in staged[b]:
+                staged[b][k].copy_(host[k], non_blocking=True)
+            ready[b].record(h2d)
+
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    prefetch(0)
+    for i in range(steps):
+        b = i & 1
+        if i + 1 < steps:
+            prefetch(i + 1)
+        cur.wait_event(ready[b])
+        if i >= 2:
+            cur.wait_event(fetched[b])          # outs[b] has been copied out
+        color = step_fn(staged[b])
+        outs[b].copy_(color.detach())
+        consumed[b].record(cur)
+        rendered[b].record(cur)
+        with torch.cuda.stream(d2h):
+            d2h.wait_event(rendered[b])
+            out_host.copy_(outs[b], non_blocking=True)
+            fetched[b].record(d2h)
+    cur.wait_stream(d2h)
+    cur.wait_stream(h2d)
+    e1.record(cur)
+    barrier()
+    return e0.elapsed_time(e1)
 
 
 def build_inputs(P, W, H, seed, device):
@@ -176,23 +226,8 @@ def run_ours(args, rank, world, device):
 
     # end-to-end: H2D of the step's inputs from pinned memory + D2H of the rendered image
     out_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
-    staged = {k: torch.empty_like(v) for k, v in dev.items()}
-
-    def e2e_step():
-        for k in staged:
-            staged[k].copy_(host[k], non_blocking=True)
-        color = step(staged)
-        out_host.copy_(color.detach(), non_blocking=True)
-
-    for _ in range(min(2, args.warmup)):
-        e2e_step()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    ms_e2e = shard.max_over_ranks(e0.elapsed_time(e1), device)
+    pipelined_e2e(step, host, dev, out_host, 2, barrier)  # warm the side streams / allocator
+    ms_e2e = shard.max_over_ranks(pipelined_e2e(step, host, dev, out_host, args.steps, barrier), device)
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = out_host.numel() * out_host.element_size()
@@ -248,17 +283,8 @@ def run_reference_cuda(args, rank, world, device):
     barrier()
     ms_resident = shard.max_over_ranks(e0.elapsed_time(e1), device)
     out_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
-    staged = {k: torch.empty_like(v) for k, v in dev.items()}
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        for k in staged:
-            staged[k].copy_(host[k], non_blocking=True)
-        color = step(staged)
-        out_host.copy_(color, non_blocking=True)
-    e1.record()
-    barrier()
-    ms_e2e = shard.max_over_ranks(e0.elapsed_time(e1), device)
+    pipelined_e2e(step, host, dev, out_host, 2, barrier)
+    ms_e2e = shard.max_over_ranks(pipelined_e2e(step, host, dev, out_host, args.steps, barrier), device)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     return dict(ms_resident=ms_resident, ms_e2e=ms_e2e, h2d=h2d, d2h=out_host.numel() * 4, R=int(state["R"]),
                 V=int((state["radii"] > 0).sum().item()))
