@@ -19,8 +19,8 @@ __global__ void surfel_preprocess_bwd(int, int, int, const float*, const float2*
                                       float*, float*, float*, float*, float*, float*);
 __global__ void mark_visible_kernel(int, const float*, const ViewParams, uint8_t*);
 __global__ void tile_scan(int, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, const int*);
-__global__ void scatter_keys(int, const GeomRec*, const CullRec*, const float*, const int*, const uint32_t*, int, int,
-                             uint32_t*, uint64_t*);
+__global__ void scatter_keys(int, const float*, const float*, int, const CullRec*, const float*, const int*,
+                             const uint32_t*, int, int, uint32_t*, uint64_t*);
 __global__ void sort_build_records(const uint32_t*, uint64_t*, const GeomRec*, const float*, int, int, int, float4*,
                                    size_t, int);
 __global__ void surfel_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float*,
@@ -262,8 +262,8 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
 
     if (R > 0) {
         prof_begin(GSR_PROF_DUPLICATE, s);
-        scatter_keys<<<(P + 255) / 256, 256, 0, s>>>(P, gw.geom, gw.cull, gw.depths, radii, gw.masks, vc.gx, vc.gy,
-                                                     iw.tile_cursor, bw.keys);
+        scatter_keys<<<(P + 255) / 256, 256, 0, s>>>(P, &gw.geom->tu.w, &gw.geom->tv.w, (int)(sizeof(GeomRec) / 4), gw.cull,
+                                                     gw.depths, radii, gw.masks, vc.gx, vc.gy, iw.tile_cursor, bw.keys);
         prof_end(GSR_PROF_DUPLICATE, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         const float* colors = colors_precomp ? colors_precomp : gw.rgb;

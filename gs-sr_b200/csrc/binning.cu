@@ -17,6 +17,7 @@
 // on which every pixel of the tile would `continue`.
 #include "common.cuh"
 #include "cull.cuh"
+#include "tile_sort.cuh"
 
 namespace gsr {
 
@@ -62,7 +63,8 @@ tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict_
 
 // ---- 3. scatter (depth, index) keys into tile buckets ---------------------------------------
 __global__ void __launch_bounds__(256)
-scatter_keys(int P, const GeomRec* __restrict__ geom, const CullRec* __restrict__ cull,
+scatter_keys(int P, const float* __restrict__ centre_x, const float* __restrict__ centre_y, int centre_stride,
+             const CullRec* __restrict__ cull,
              const float* __restrict__ depths, const int* __restrict__ radii, const uint32_t* __restrict__ masks, int gx, int gy,
              uint32_t* __restrict__ cursors, uint64_t* __restrict__ keys) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,7 +73,8 @@ scatter_keys(int P, const GeomRec* __restrict__ geom, const CullRec* __restrict_
     if (r <= 0) return;
     const uint32_t mask = masks[idx];
     if (mask == 0u) return;
-    const float cx = geom[idx].tu.w, cy = geom[idx].tv.w;
+    // screen centre the rect was built from: a strided view into the variant's per-Gaussian record
+    const float cx = centre_x[(size_t)idx * centre_stride], cy = centre_y[(size_t)idx * centre_stride];
     const uint64_t key = ((uint64_t)__float_as_uint(depths[idx]) << 32) | (uint32_t)idx;
     int x0, y0, x1, y1;
     get_rect(cx, cy, r, gx, gy, x0, y0, x1, y1);
@@ -94,43 +97,6 @@ scatter_keys(int P, const GeomRec* __restrict__ geom, const CullRec* __restrict_
 }
 
 // ---- 4. per-tile sort fused with record materialisation --------------------------------------
-constexpr int SORT_SMEM_CAP = 4096;            // keys sorted in shared memory (32 KB)
-constexpr uint64_t KEY_INF = ~0ull;
-
-// All-ascending bitonic network on m = pow2 >= n virtual slots; slots >= n hold +inf and are
-// never materialised when sorting in global memory (a compare against them is a no-op).
-template <bool kShared>
-__device__ __forceinline__ void bitonic_sort(uint64_t* __restrict__ k, int n, int m) {
-    for (int lsize = 1; (1 << lsize) <= m; lsize++) {
-        const int size = 1 << lsize;
-        for (int ls = lsize - 1; ls >= 0; ls--) {
-            const int stride = 1 << ls;
-            const bool first = (ls == lsize - 1);
-            // comparators are handled two at a time per thread (all four loads first: ILP)
-            for (int t0 = threadIdx.x; t0 < (m >> 1); t0 += 2 * blockDim.x) {
-                const int t1 = t0 + blockDim.x;
-                // t-th comparator of this step: lower index lo, partner hi > lo
-                const int lo0 = ((t0 >> ls) << (ls + 1)) | (t0 & (stride - 1));
-                const int hi0 = first ? (lo0 ^ (size - 1)) : (lo0 | stride);
-                const int lo1 = ((t1 >> ls) << (ls + 1)) | (t1 & (stride - 1));
-                const int hi1 = first ? (lo1 ^ (size - 1)) : (lo1 | stride);
-                const bool ok0 = kShared || hi0 < n, ok1 = (t1 < (m >> 1)) && (kShared || hi1 < n);
-                uint64_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-                if (ok0) { a0 = k[lo0]; b0 = k[hi0]; }
-                if (ok1) { a1 = k[lo1]; b1 = k[hi1]; }
-                if (ok0 && a0 > b0) { k[lo0] = b0; k[hi0] = a0; }
-                if (ok1 && a1 > b1) { k[lo1] = b1; k[hi1] = a1; }
-            }
-            // comparators t = 32w .. 32w+31 of a step with stride <= 32 only touch the 64-slot
-            // window [64w, 64w+64): a warp-level sync suffices when this step wrote and the next
-            // step reads inside that window
-            const int next_stride = ls > 0 ? (stride >> 1) : size;
-            if (kShared && stride <= 32 && next_stride <= 32) __syncwarp();
-            else __syncthreads();
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256)
 sort_build_records(const uint32_t* __restrict__ offsets, uint64_t* __restrict__ keys,
                    const GeomRec* __restrict__ geom,

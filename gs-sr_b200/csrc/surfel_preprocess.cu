@@ -14,14 +14,10 @@
 #include "common.cuh"
 #include "sh.cuh"
 #include "cull.cuh"
+#include "pinned.cuh"
 #include "../../include/gsr_b200.h"
 
 namespace gsr {
-
-__device__ __forceinline__ void load16(const float* __restrict__ src, float* dst) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) dst[i] = __ldg(src + i);
-}
 
 // quat (w,x,y,z) -> rotation columns, normalised in-kernel (S/auxiliary.h:215-237)
 __device__ __forceinline__ void quat_to_rot(float4 q, float3& c0, float3& c1, float3& c2) {
@@ -32,26 +28,6 @@ __device__ __forceinline__ void quat_to_rot(float4 q, float3& c0, float3& c1, fl
     c2 = make_float3(2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y));
 }
 
-// ---- pinned float32 sequences ------------------------------------------------------------
-// radius = ceil(sqrt(p^2 - f.(T o T))) cancels ~4 digits in global pixel coordinates and the
-// sort key is the raw bits of the view depth, so radii / tile lists / ordering only match the
-// reference if T, the AABB and p_view are rounded EXACTLY as its build rounds them.  The
-// sequences below were read off the SASS nvcc 12.9 emits for the unmodified reference
-// (cuobjdump of oracle/_ref/libref_surfel.so): every  a*x + b*y + c*z (+ d)  is evaluated as
-//     fma(c, z, fma(a, x, rn(b*y)))  (+ d with a separate add),
-// and explicit intrinsics keep the compiler from re-contracting them here.
-__device__ __forceinline__ float dot_yxz(float a, float x, float b, float y, float c, float z) {
-    return __fmaf_rn(c, z, __fmaf_rn(a, x, __fmul_rn(b, y)));
-}
-__device__ __forceinline__ float3 xform43_pinned(const float* __restrict__ m, float3 p) {
-    return make_float3(__fadd_rn(dot_yxz(p.x, m[0], p.y, m[4], p.z, m[8]), m[12]),
-                       __fadd_rn(dot_yxz(p.x, m[1], p.y, m[5], p.z, m[9]), m[13]),
-                       __fadd_rn(dot_yxz(p.x, m[2], p.y, m[6], p.z, m[10]), m[14]));
-}
-__device__ __forceinline__ float3 xformvec43_pinned(const float* __restrict__ m, float3 p) {
-    return make_float3(dot_yxz(p.x, m[0], p.y, m[4], p.z, m[8]), dot_yxz(p.x, m[1], p.y, m[5], p.z, m[9]),
-                       dot_yxz(p.x, m[2], p.y, m[6], p.z, m[10]));
-}
 // quat (w,x,y,z) -> rotation columns, S/auxiliary.h:215-237, in the reference build's rounding
 __device__ __forceinline__ void quat_to_rot_pinned(float4 q, float3& c0, float3& c1, float3& c2) {
     const float sum = __fmaf_rn(q.z, q.z, __fmaf_rn(q.y, q.y, __fmaf_rn(q.x, q.x, __fmul_rn(q.w, q.w))));

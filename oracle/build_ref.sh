@@ -48,7 +48,7 @@ if [ -f "$HERE/ref_driver_filter.cu" ]; then
         echo "build_ref: building $so"
         nvcc -O3 $ARCH -std=c++17 -lineinfo -include cstdint -Xcompiler -fPIC -shared -w \
             -I "$sub" -I "$sub/third_party/glm" \
-            "$sub/cuda_rasterizer/forward.cu" "$sub/cuda_rasterizer/backward.cu" \
+            "$sub/cuda_rasterizer/forward.cu" \
             "$sub/cuda_rasterizer/rasterizer_impl.cu" "$HERE/ref_driver_filter.cu" -o "$so"
     fi
 fi

@@ -118,4 +118,104 @@ int ref_backward(void* h, int P, int D, int M, const float* bg, int W, int H,
 }
 #endif  // REF_VARIANT_SURFEL
 
+#if defined(REF_VARIANT_GAUSSIAN)
+// mirrors RasterizeGaussiansCUDA (G/rasterize_points.cu:35-113); outputs zero-filled by the caller.
+int ref_forward(void* h, int P, int D, int M, const float* bg, int W, int H,
+                const float* means3D, const float* shs, const float* colors_precomp,
+                const float* opacities, const float* scales, float scale_modifier,
+                const float* rotations, const float* cov3D_precomp,
+                const float* viewmatrix, const float* projmatrix, const float* campos,
+                float tan_fovx, float tan_fovy, int prefiltered,
+                float* out_color, int* radii, int debug) {
+    RefHandle* r = (RefHandle*)h;
+    r->num_rendered = 0;
+    if (P == 0) return 0;
+    std::function<char*(size_t)> g = [r](size_t n) { return r->geom.get(n); };
+    std::function<char*(size_t)> b = [r](size_t n) { return r->binning.get(n); };
+    std::function<char*(size_t)> i = [r](size_t n) { return r->img.get(n); };
+    try {
+        r->num_rendered = CudaRasterizer::Rasterizer::forward(
+            g, b, i, P, D, M, bg, W, H, means3D, shs, colors_precomp, opacities, scales,
+            scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos,
+            tan_fovx, tan_fovy, prefiltered != 0, out_color, radii, debug != 0);
+    } catch (...) { return -1; }
+    return (int)cudaGetLastError();
+}
+
+// mirrors RasterizeGaussiansBackwardCUDA (G/rasterize_points.cu:115-197); dL_* zero-filled by the caller.
+int ref_backward(void* h, int P, int D, int M, const float* bg, int W, int H,
+                 const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* scales, float scale_modifier, const float* rotations,
+                 const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+                 const int* radii, const float* dL_dpix,
+                 float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                 float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
+                 float* dL_drot, int debug) {
+    RefHandle* r = (RefHandle*)h;
+    if (P == 0) return 0;
+    try {
+        CudaRasterizer::Rasterizer::backward(
+            P, D, M, r->num_rendered, bg, W, H, means3D, shs, colors_precomp, scales,
+            scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos,
+            tan_fovx, tan_fovy, radii, r->geom.ptr, r->binning.ptr, r->img.ptr, dL_dpix,
+            dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
+            dL_dscale, dL_drot, debug != 0);
+    } catch (...) { return -1; }
+    return (int)cudaGetLastError();
+}
+#endif  // REF_VARIANT_GAUSSIAN
+
+#if defined(REF_VARIANT_PLANE)
+// mirrors RasterizeGaussiansCUDA (L/rasterize_points.cu:35-125); outputs zero-filled by the caller.
+int ref_forward(void* h, int P, int D, int M, const float* bg, int W, int H,
+                const float* means3D, const float* shs, const float* colors_precomp,
+                const float* opacities, const float* scales, float scale_modifier,
+                const float* rotations, const float* cov3D_precomp, const float* all_map,
+                const float* viewmatrix, const float* projmatrix, const float* campos,
+                float tan_fovx, float tan_fovy, int prefiltered,
+                float* out_color, int* radii, int* out_observe, float* out_all_map,
+                float* out_plane_depth, int render_geo, int debug) {
+    RefHandle* r = (RefHandle*)h;
+    r->num_rendered = 0;
+    if (P == 0) return 0;
+    std::function<char*(size_t)> g = [r](size_t n) { return r->geom.get(n); };
+    std::function<char*(size_t)> b = [r](size_t n) { return r->binning.get(n); };
+    std::function<char*(size_t)> i = [r](size_t n) { return r->img.get(n); };
+    try {
+        r->num_rendered = CudaRasterizer::Rasterizer::forward(
+            g, b, i, P, D, M, bg, W, H, means3D, shs, colors_precomp, opacities, scales,
+            scale_modifier, rotations, cov3D_precomp, all_map, viewmatrix, projmatrix, campos,
+            tan_fovx, tan_fovy, prefiltered != 0, out_color, radii, out_observe, out_all_map,
+            out_plane_depth, render_geo != 0, debug != 0);
+    } catch (...) { return -1; }
+    return (int)cudaGetLastError();
+}
+
+// mirrors RasterizeGaussiansBackwardCUDA (L/rasterize_points.cu:127-231); dL_* zero-filled by the caller.
+int ref_backward(void* h, int P, int D, int M, const float* bg, const float* all_map_pixels, int W, int H,
+                 const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* all_maps, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+                 const int* radii, const float* dL_dpix, const float* dL_dout_all_map,
+                 const float* dL_dout_plane_depth, float* dL_dmean2D, float* dL_dmean2D_abs,
+                 float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                 float* dL_dall_map, int render_geo, int debug) {
+    RefHandle* r = (RefHandle*)h;
+    if (P == 0) return 0;
+    try {
+        CudaRasterizer::Rasterizer::backward(
+            P, D, M, r->num_rendered, bg, all_map_pixels, W, H, means3D, shs, colors_precomp, all_maps,
+            scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos,
+            tan_fovx, tan_fovy, radii, r->geom.ptr, r->binning.ptr, r->img.ptr, dL_dpix,
+            dL_dout_all_map, dL_dout_plane_depth, dL_dmean2D, dL_dmean2D_abs, dL_dconic, dL_dopacity,
+            dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dall_map,
+            render_geo != 0, debug != 0);
+    } catch (...) { return -1; }
+    return (int)cudaGetLastError();
+}
+#endif  // REF_VARIANT_PLANE
+
 }  // extern "C"

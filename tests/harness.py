@@ -161,3 +161,133 @@ def compare_grads(a, b, names=("a", "b"), verbose=True):
         for k, v in res.items():
             print(f"   {k:12s} {v[0]:.3e} {v[1]:.3e}")
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# 3DGS (diff_gaussian_rasterization) and PGSR plane (diff_plane_rasterization) variants
+# ---------------------------------------------------------------------------------------------
+GAUSS_GRAD_KEYS = ("means3D", "means2D", "means2D_abs", "shs", "colors", "opacities", "scales", "rotations",
+                   "cov3D", "all_map")
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def run_product_gauss(scene, g_color=None, plane=False, all_map=None, g_all_map=None, g_plane_depth=None,
+                      cov3D_precomp=None, scale_modifier=1.0, render_geo=True, device="cuda", tt=None):
+    """Forward (+ backward) through the drop-in diff_gaussian_rasterization / diff_plane_rasterization API."""
+    import torch
+    if plane:
+        from diff_plane_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    else:
+        from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    cam = scene.cam
+    tt = tt or to_torch(scene, device)
+    leaves = {}
+    for k in ("means3D", "scales", "rotations", "opacities", "colors", "shs"):
+        if tt[k] is not None:
+            leaves[k] = tt[k].clone().requires_grad_(True)
+    if cov3D_precomp is not None:
+        leaves["cov3D"] = torch.from_numpy(cov3D_precomp).to(device).requires_grad_(True)
+        leaves.pop("scales", None); leaves.pop("rotations", None)
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    kw = dict(image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=tt["bg"],
+              scale_modifier=scale_modifier, viewmatrix=tt["view"], projmatrix=tt["proj"],
+              sh_degree=scene.sh_degree, campos=tt["campos"], prefiltered=False, debug=False)
+    if plane:
+        kw["render_geo"] = render_geo
+    rast = GaussianRasterizer(GaussianRasterizationSettings(**kw))
+    common = dict(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], shs=leaves.get("shs"),
+                  colors_precomp=leaves.get("colors"), scales=leaves.get("scales"),
+                  rotations=leaves.get("rotations"), cov3D_precomp=leaves.get("cov3D"))
+    if plane:
+        means2D_abs = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        if all_map is not None:
+            leaves["all_map"] = torch.from_numpy(all_map).to(device).requires_grad_(True)
+        color, radii, observe, out_all_map, plane_depth = rast(means2D_abs=means2D_abs,
+                                                               all_map=leaves.get("all_map"), **common)
+        out = dict(color=_np(color), radii=_np(radii), observe=_np(observe), out_all_map=_np(out_all_map),
+                   plane_depth=_np(plane_depth))
+    else:
+        color, radii = rast(**common)
+        out = dict(color=_np(color), radii=_np(radii))
+    if g_color is not None:
+        outs, gs = [color], [torch.from_numpy(g_color).to(device)]
+        if plane and render_geo and g_all_map is not None:
+            outs += [out_all_map, plane_depth]
+            gs += [torch.from_numpy(g_all_map).to(device), torch.from_numpy(g_plane_depth).to(device)]
+        torch.autograd.backward(outs, gs)
+        grads = {"means2D": means2D.grad}
+        if plane:
+            grads["means2D_abs"] = means2D_abs.grad
+        for k, v in leaves.items():
+            grads[k] = v.grad
+        out["grads"] = {k: _np(v) for k, v in grads.items()}
+    return out
+
+
+def run_oracle_gauss(scene, g_color=None, plane=False, all_map=None, g_all_map=None, g_plane_depth=None,
+                     cov3D_precomp=None, scale_modifier=1.0, render_geo=True, double=False):
+    from oracle.oracle import GaussOracle
+    o = GaussOracle(plane=plane, double=double)
+    pre = cov3D_precomp is not None
+    out = o.forward(scene.cam, scene.means3D, scene.opacities, None if pre else scene.scales,
+                    None if pre else scene.rotations, colors=scene.colors, shs=scene.shs,
+                    sh_degree=scene.sh_degree, cov3D_precomp=cov3D_precomp, all_map=all_map,
+                    scale_modifier=scale_modifier, render_geo=render_geo)
+    out["oracle"] = o
+    if g_color is not None:
+        out["grads"] = o.backward(g_color, g_all_map, g_plane_depth)
+    return out
+
+
+def run_refcuda_gauss(scene, g_color=None, plane=False, all_map=None, g_all_map=None, g_plane_depth=None,
+                      cov3D_precomp=None, scale_modifier=1.0, render_geo=True, device="cuda", tt=None):
+    import torch
+    from oracle.refcuda import RefGauss
+    cam = scene.cam
+    tt = tt or to_torch(scene, device)
+    r = RefGauss(plane=plane)
+    pre = None if cov3D_precomp is None else torch.from_numpy(cov3D_precomp).to(device)
+    am = None if all_map is None else torch.from_numpy(all_map).to(device)
+    f = r.forward(tt["bg"], tt["view"], tt["proj"], tt["campos"], cam.W, cam.H, cam.tanfovx, cam.tanfovy,
+                  tt["means3D"], tt["opacities"], None if pre is not None else tt["scales"],
+                  None if pre is not None else tt["rotations"], colors=tt["colors"], shs=tt["shs"],
+                  sh_degree=scene.sh_degree, cov3D_precomp=pre, all_map=am, scale_modifier=scale_modifier,
+                  render_geo=render_geo)
+    torch.cuda.synchronize()
+    out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in f.items()}
+    out["ref"] = r
+    if g_color is not None:
+        gam = None if g_all_map is None else torch.from_numpy(g_all_map).to(device)
+        gpd = None if g_plane_depth is None else torch.from_numpy(g_plane_depth).to(device)
+        g = r.backward(torch.from_numpy(g_color).to(device), gam, gpd)
+        torch.cuda.synchronize()
+        out["grads"] = {k: v.cpu().numpy() for k, v in g.items()}
+    return out
+
+
+def compare_grads_keys(a, b, keys, names=("a", "b"), verbose=True, outlier_frac=0.0):
+    """rel-Linf / rel-L2 per gradient tensor; with outlier_frac the rows (Gaussians) with the largest
+    deviation are excluded first (same rule as tests/test_oracle_golden.py)."""
+    res = {}
+    for k in keys:
+        if k not in a or k not in b or a[k] is None or b[k] is None or np.size(b[k]) == 0:
+            continue
+        x, y = np.asarray(a[k], np.float64), np.asarray(b[k], np.float64)
+        y = y.reshape(x.shape)
+        d = np.abs(x - y).reshape(x.shape[0], -1).max(axis=1)
+        keep = np.ones(x.shape[0], bool)
+        if outlier_frac > 0:
+            kdrop = int(np.ceil(outlier_frac * x.shape[0]))
+            if 0 < kdrop < x.shape[0]:
+                keep[np.argsort(d)[-kdrop:]] = False
+        linf = float(d[keep].max() / max(np.abs(y).max(), 1e-30))
+        l2 = float(np.linalg.norm((x - y)[keep]) / max(np.linalg.norm(y), 1e-30))
+        res[k] = (linf, l2)
+    if verbose:
+        print(f"grads {names[0]} vs {names[1]}:  (rel Linf, rel L2)")
+        for k, v in res.items():
+            print(f"   {k:12s} {v[0]:.3e} {v[1]:.3e}")
+    return res

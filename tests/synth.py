@@ -148,3 +148,42 @@ def make_upstream_grads(W, H, seed=1, n_others=11, zero_from=7, n_color=3):
     g_others = (rng.normal(size=(n_others, H, W)) / n).astype(np.float32)
     g_others[zero_from:] = 0
     return g_color, g_others
+
+
+def make_all_map(scene):
+    """Per-Gaussian PGSR input [n_view(3), 1.0, |n_view . p_view|] as built by the caller
+    (/root/reference/gssr/scene/pgsr_scene.py:241-302): normal = smallest-scale rotation axis,
+    flipped to face the camera, expressed in the view frame (row-vector convention)."""
+    view = scene.cam.viewmatrix.astype(np.float64)
+    q = scene.rotations.astype(np.float64)
+    q = q / np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    Rm = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], -1),
+                   np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], -1),
+                   np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1)], 1)
+    k = scene.scales.argmin(axis=1)
+    n = Rm[np.arange(scene.P), :, k]
+    to_cam = scene.cam.campos.astype(np.float64)[None] - scene.means3D
+    n[(n * to_cam).sum(-1) < 0] *= -1
+    ln = n @ view[:3, :3]
+    pc = scene.means3D.astype(np.float64) @ view[:3, :3] + view[3, :3]
+    am = np.zeros((scene.P, 5), np.float32)
+    am[:, :3] = ln
+    am[:, 3] = 1.0
+    am[:, 4] = np.abs((ln * pc).sum(-1))
+    return am
+
+
+def make_points(P, seed=0, clustered=False):
+    """Point clouds for distCUDA2: uniform box or a mixture of tight clusters + duplicates."""
+    rng = np.random.default_rng(seed)
+    if not clustered:
+        return rng.uniform(-3, 3, size=(P, 3)).astype(np.float32)
+    k = max(4, P // 200)
+    cen = rng.uniform(-5, 5, size=(k, 3))
+    idx = rng.integers(0, k, size=P)
+    pts = cen[idx] + rng.normal(0, 0.05, size=(P, 3)) * rng.uniform(0.1, 3.0, size=(k, 1))[idx]
+    pts = pts.astype(np.float32)
+    nd = max(1, P // 50)
+    pts[rng.integers(0, P, nd)] = pts[rng.integers(0, P, nd)]   # exact duplicates (distance 0)
+    return pts
