@@ -5,6 +5,7 @@
 #include <cstring>
 #include <chrono>
 #include "common.cuh"
+#include "ewa_common.cuh"
 #include "../../include/gsr_b200.h"
 
 namespace gsr {
@@ -27,6 +28,23 @@ __global__ void surfel_render_fwd(const uint32_t*, const float4*, size_t, int, i
                                   uint32_t*, float*, float*);
 __global__ void surfel_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*,
                                   const float*, const uint32_t*, const float*, const float*, float*);
+template <bool kRadiiOnly>
+__global__ void ewa_preprocess_fwd(int, int, int, const float*, const float*, const float4*, const float*, const float*,
+                                   const float*, const bool, const ViewParams, const float, const float, const float,
+                                   const float, const bool, const bool, int*, EwaGeom*, CullRec*, float*, uint32_t*,
+                                   uint32_t*, float*, uint8_t*, int*);
+__global__ void ewa_preprocess_bwd(int, int, int, const float*, const float*, const float4*, const float*, const float*,
+                                   const ViewParams, const float, const float, const float, const float, const int*,
+                                   const uint8_t*, const float*, float*, float*, float*, float*, float*, float*, float*,
+                                   float*, float*, float*, float*);
+template <bool GEO>
+__global__ void ewa_build_records(const uint32_t*, uint64_t*, const EwaGeom*, const float*, const float*, int, float4*, size_t);
+template <bool GEO>
+__global__ void ewa_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float, float*,
+                               uint32_t*, float*, int*, float*, float*);
+template <int MODE>
+__global__ void ewa_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
+                               const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
 // ---- error string -------------------------------------------------------------
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -49,24 +67,37 @@ size_t GeomWs::carve(GeomWs& w, char* base, int P) {
     w.flags = c.take<int>(32);
     return c.used + 256;
 }
-size_t ImageWs::carve(ImageWs& w, char* base, int W, int H) {
+size_t ImageWs::carve(ImageWs& w, char* base, int W, int H, int nT, int nC) {
     Carver c(base);
     size_t N = (size_t)W * H;
     size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
-    w.final_T = c.take<float>(3 * N);
-    w.n_contrib = c.take<uint32_t>(2 * N);
+    w.final_T = c.take<float>(nT * N);
+    w.n_contrib = c.take<uint32_t>(nC * N);
     w.tile_count = c.take<uint32_t>(tiles + 2);
     w.tile_offset = c.take<uint32_t>(tiles + 1);
     w.tile_cursor = c.take<uint32_t>(tiles);
     return c.used + 256;
 }
-size_t BinWs::carve(BinWs& w, char* base, int64_t R, int P) {
+size_t BinWs::carve(BinWs& w, char* base, int64_t R, int P, int nplanes, int gacc_stride) {
     Carver c(base);
     size_t n = R > 0 ? (size_t)R : 1;
     w.keys = c.take<uint64_t>(n);
     w.plane_stride = (n + 7) & ~size_t(7);
-    w.planes = c.take<float4>(w.plane_stride * REC_PLANES);
-    w.gacc = c.take<float>((size_t)(P > 0 ? P : 1) * GACC_STRIDE);
+    w.planes = c.take<float4>(w.plane_stride * nplanes);
+    w.gacc = c.take<float>((size_t)(P > 0 ? P : 1) * gacc_stride);
+    return c.used + 256;
+}
+
+size_t EwaGeomWs::carve(EwaGeomWs& w, char* base, int P) {
+    Carver c(base);
+    size_t n = P > 0 ? (size_t)P : 1;
+    w.geom = c.take<EwaGeom>(n);
+    w.cull = c.take<CullRec>(n);
+    w.depths = c.take<float>(n);
+    w.masks = c.take<uint32_t>(n);
+    w.rgb = c.take<float>(3 * n);
+    w.clamped = c.take<uint8_t>(3 * n);
+    w.flags = c.take<int>(32);
     return c.used + 256;
 }
 
@@ -343,6 +374,299 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
     const ViewParams vc = make_view(viewmatrix, projmatrix, nullptr, 0, 0, 1.0f);
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, vc, present);
     GSR_CUDA_CHECK(cudaGetLastError());
+    return GSR_OK;
+}
+
+}  // extern "C"
+
+// ---- EWA family (3DGS + PGSR plane): shared host orchestration ------------------------------------
+namespace gsr {
+static int g_last_R_ewa = 0;
+
+struct EwaFwdArgs {
+    gsr_buffer_fn geometryBuffer, binningBuffer, imageBuffer;
+    void* user;
+    int P, D, M;
+    const float* background;
+    int W, H;
+    const float *means3D, *shs, *colors_precomp, *opacities, *scales;
+    float scale_modifier;
+    const float *rotations, *cov3D_precomp, *all_map, *viewmatrix, *projmatrix, *cam_pos;
+    float tan_fovx, tan_fovy;
+    int prefiltered;
+    float* out_color;
+    int* radii;
+    int* out_observe;         // plane only (else NULL)
+    float *out_all_map, *out_plane_depth;
+    bool plane, geo;
+    int debug;
+    cudaStream_t s;
+};
+
+static int ewa_forward(const EwaFwdArgs& a, const char* who) {
+    cudaStream_t s = a.s;
+    const int P = a.P, W = a.W, H = a.H;
+    if (P < 0 || W <= 0 || H <= 0 || !a.out_color || !a.background || !a.viewmatrix || !a.projmatrix) {
+        set_error("%s: invalid argument", who); return GSR_E_INVALID;
+    }
+    if (P > 0 && (!a.means3D || !a.opacities || !a.radii)) { set_error("%s: means3D/opacities/radii required", who); return GSR_E_INVALID; }
+    if (P > 0 && ((a.shs == nullptr) == (a.colors_precomp == nullptr))) { set_error("provide exactly one of shs / colors_precomp"); return GSR_E_INVALID; }
+    if (P > 0 && (((a.scales == nullptr) || (a.rotations == nullptr)) == (a.cov3D_precomp == nullptr))) { set_error("provide exactly one of scales+rotations / cov3D_precomp"); return GSR_E_INVALID; }
+    if (P > 0 && a.shs && !a.cam_pos) { set_error("cam_pos required with shs"); return GSR_E_INVALID; }
+    if (a.plane && (!a.out_observe || (a.geo && (!a.out_all_map || !a.out_plane_depth || (P > 0 && !a.all_map))))) {
+        set_error("%s: out_observe / out_all_map / out_plane_depth / all_map required", who); return GSR_E_INVALID;
+    }
+    const size_t N = (size_t)W * H;
+    const ViewParams vc = make_view(a.viewmatrix, a.projmatrix, a.cam_pos, W, H, a.scale_modifier);
+    const int ntiles = vc.gx * vc.gy;
+    const float focal_y = (float)H / (2.0f * a.tan_fovy), focal_x = (float)W / (2.0f * a.tan_fovx);   // G/rasterizer_impl.cu:223-224
+    const int nplanes = a.geo ? EWA_PLANES_GEO : EWA_PLANES;
+
+    ImageWs iw;
+    size_t ibytes = ImageWs::carve(iw, nullptr, W, H, 1, 1);
+    char* ibase = a.imageBuffer(a.user, ibytes);
+    if (!ibase) { set_error("imageBuffer callback failed (%zu bytes)", ibytes); return GSR_E_ALLOC; }
+    ImageWs::carve(iw, align256(ibase), W, H, 1, 1);
+    GSR_CUDA_CHECK(cudaMemsetAsync(iw.tile_count, 0, (size_t)((char*)(iw.tile_cursor + ntiles) - (char*)iw.tile_count), s));
+    if (a.plane && P > 0) GSR_CUDA_CHECK(cudaMemsetAsync(a.out_observe, 0, (size_t)P * sizeof(int), s));
+    if (a.plane && !a.geo) {   // torch::full(..., 0) in the reference glue (L/rasterize_points.cu:75-76)
+        if (a.out_all_map) GSR_CUDA_CHECK(cudaMemsetAsync(a.out_all_map, 0, NUM_ALL_MAP * N * sizeof(float), s));
+        if (a.out_plane_depth) GSR_CUDA_CHECK(cudaMemsetAsync(a.out_plane_depth, 0, N * sizeof(float), s));
+    }
+
+    int R = 0;
+    EwaGeomWs gw;
+    BinWs bw;
+    memset(&bw, 0, sizeof(bw));
+    memset(&gw, 0, sizeof(gw));
+    if (P > 0) {
+        size_t gbytes = EwaGeomWs::carve(gw, nullptr, P);
+        char* gbase = a.geometryBuffer(a.user, gbytes);
+        if (!gbase) { set_error("geometryBuffer callback failed (%zu bytes)", gbytes); return GSR_E_ALLOC; }
+        EwaGeomWs::carve(gw, align256(gbase), P);
+        GSR_CUDA_CHECK(cudaMemsetAsync(gw.flags, 0, 32 * sizeof(int), s));
+        prof_begin(GSR_PROF_PREPROCESS_FWD, s);
+        ewa_preprocess_fwd<false><<<(P + 255) / 256, 256, 0, s>>>(
+            P, a.D, a.M, a.means3D, a.scales, (const float4*)a.rotations, a.opacities, a.shs, a.cov3D_precomp,
+            a.colors_precomp != nullptr, vc, focal_x, focal_y, a.tan_fovx, a.tan_fovy, a.prefiltered != 0, no_cull(),
+            a.radii, gw.geom, gw.cull, gw.depths, gw.masks, iw.tile_count, gw.rgb, gw.clamped, gw.flags);
+        prof_end(GSR_PROF_PREPROCESS_FWD, s);
+        GSR_CUDA_CHECK(cudaGetLastError());
+        prof_begin(GSR_PROF_SCAN, s);
+        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.tile_count + ntiles, gw.flags);
+        prof_end(GSR_PROF_SCAN, s);
+        GSR_CUDA_CHECK(cudaGetLastError());
+        // speculative binning buffer before the read-back (see gsr_surfel_forward)
+        const int R_guess = g_last_R_ewa > 0 ? (int)fmin(2.0e9, 1.25 * (double)g_last_R_ewa + 4096.0) : 0;
+        char* bbase = nullptr;
+        size_t bcap = 0;
+        if (R_guess > 0) {
+            bcap = BinWs::carve(bw, nullptr, R_guess, P, nplanes, EWA_GACC);
+            bbase = a.binningBuffer(a.user, bcap);
+            if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bcap); return GSR_E_ALLOC; }
+        }
+        uint32_t rb[2] = {0u, 0u};
+        GSR_CUDA_CHECK(cudaMemcpyAsync(rb, iw.tile_count + ntiles, 8, cudaMemcpyDeviceToHost, s));
+        GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (rb[1]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
+        if (rb[0] > 0x7fffff00u) { set_error("num_rendered overflow (%u)", rb[0]); return GSR_E_OVERFLOW; }
+        R = (int)rb[0];
+        g_last_R_ewa = R;
+        size_t bbytes = BinWs::carve(bw, nullptr, R, P, nplanes, EWA_GACC);
+        if (!bbase || bbytes > bcap) {
+            bbase = a.binningBuffer(a.user, bbytes);
+            if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
+        }
+        BinWs::carve(bw, align256(bbase), R, P, nplanes, EWA_GACC);
+    } else {
+        size_t bbytes = BinWs::carve(bw, nullptr, 0, 0, nplanes, EWA_GACC);
+        char* bbase = a.binningBuffer(a.user, bbytes);
+        if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
+        BinWs::carve(bw, align256(bbase), 0, 0, nplanes, EWA_GACC);
+    }
+    if (R > 0) {
+        prof_begin(GSR_PROF_DUPLICATE, s);
+        scatter_keys<<<(P + 255) / 256, 256, 0, s>>>(P, &gw.geom->a.x, &gw.geom->a.y, (int)(sizeof(EwaGeom) / 4), gw.cull,
+                                                     gw.depths, a.radii, gw.masks, vc.gx, vc.gy, iw.tile_cursor, bw.keys);
+        prof_end(GSR_PROF_DUPLICATE, s);
+        GSR_CUDA_CHECK(cudaGetLastError());
+        const float* colors = a.colors_precomp ? a.colors_precomp : gw.rgb;
+        prof_begin(GSR_PROF_BUILD_RECORDS, s);
+        if (a.geo) ewa_build_records<true><<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, a.all_map, vc.gx, bw.planes, bw.plane_stride);
+        else ewa_build_records<false><<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, nullptr, vc.gx, bw.planes, bw.plane_stride);
+        prof_end(GSR_PROF_BUILD_RECORDS, s);
+        GSR_CUDA_CHECK(cudaGetLastError());
+    }
+    prof_begin(GSR_PROF_RENDER_FWD, s);
+    if (a.geo) ewa_render_fwd<true><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+                                                                iw.final_T, iw.n_contrib, a.out_color, a.out_observe, a.out_all_map, a.out_plane_depth);
+    else ewa_render_fwd<false><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+                                                           iw.final_T, iw.n_contrib, a.out_color, a.plane ? a.out_observe : nullptr, nullptr, nullptr);
+    prof_end(GSR_PROF_RENDER_FWD, s);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    if (a.debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return R;
+}
+
+struct EwaBwdArgs {
+    int P, D, M, R;
+    const float* background;
+    const float* all_map_pixels;
+    int W, H;
+    const float *means3D, *shs, *all_maps, *scales;
+    float scale_modifier;
+    const float *rotations, *cov3D_precomp, *viewmatrix, *projmatrix, *campos;
+    float tan_fovx, tan_fovy;
+    const int* radii;
+    char *geom_buffer, *binning_buffer, *image_buffer;
+    const float *dL_dpix, *dL_dout_all_map, *dL_dout_plane_depth;
+    float *dL_dmean2D, *dL_dmean2D_abs, *dL_dconic, *dL_dopacity, *dL_dcolor, *dL_dmean3D, *dL_dcov3D, *dL_dsh,
+        *dL_dscale, *dL_drot, *dL_dall_map;
+    bool plane, geo;
+    int debug;
+    cudaStream_t s;
+};
+
+static int ewa_backward(const EwaBwdArgs& a, const char* who) {
+    cudaStream_t s = a.s;
+    const int P = a.P, W = a.W, H = a.H, R = a.R;
+    if (P == 0) return GSR_OK;
+    if (P < 0 || R < 0 || !a.geom_buffer || !a.binning_buffer || !a.image_buffer || !a.dL_dpix || !a.dL_dmean2D ||
+        !a.dL_dopacity || !a.dL_dcolor || !a.dL_dmean3D || !a.dL_dcov3D || !a.radii || !a.means3D || !a.background) {
+        set_error("%s: invalid argument", who); return GSR_E_INVALID;
+    }
+    if (a.M > 0 && a.shs && !a.dL_dsh) { set_error("dL_dsh required with shs"); return GSR_E_INVALID; }
+    if (a.plane && (!a.dL_dmean2D_abs || !a.dL_dall_map)) { set_error("%s: dL_dmean2D_abs / dL_dall_map required", who); return GSR_E_INVALID; }
+    if (a.geo && (!a.all_map_pixels || !a.dL_dout_all_map || !a.dL_dout_plane_depth || !a.all_maps)) {
+        set_error("%s: all_map_pixels / dL_dout_all_map / dL_dout_plane_depth / all_maps required with render_geo", who); return GSR_E_INVALID;
+    }
+    const ViewParams vc = make_view(a.viewmatrix, a.projmatrix, a.campos, W, H, a.scale_modifier);
+    const int ntiles = vc.gx * vc.gy;
+    const float focal_y = (float)H / (2.0f * a.tan_fovy), focal_x = (float)W / (2.0f * a.tan_fovx);   // G/rasterizer_impl.cu:369-370
+    const int nplanes = a.geo ? EWA_PLANES_GEO : EWA_PLANES;
+    EwaGeomWs gw; ImageWs iw; BinWs bw;
+    EwaGeomWs::carve(gw, align256(a.geom_buffer), P);
+    ImageWs::carve(iw, align256(a.image_buffer), W, H, 1, 1);
+    BinWs::carve(bw, align256(a.binning_buffer), R, P, nplanes, EWA_GACC);
+
+    GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * EWA_GACC * sizeof(float), s));
+    if (R > 0) {
+        prof_begin(GSR_PROF_RENDER_BWD, s);
+        if (a.geo)
+            ewa_render_bwd<2><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+                                                          iw.final_T, iw.n_contrib, a.all_map_pixels, a.dL_dpix, a.dL_dout_all_map,
+                                                          a.dL_dout_plane_depth, bw.gacc);
+        else if (a.plane)
+            ewa_render_bwd<1><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+                                                          iw.final_T, iw.n_contrib, nullptr, a.dL_dpix, nullptr, nullptr, bw.gacc);
+        else
+            ewa_render_bwd<0><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+                                                          iw.final_T, iw.n_contrib, nullptr, a.dL_dpix, nullptr, nullptr, bw.gacc);
+        prof_end(GSR_PROF_RENDER_BWD, s);
+        GSR_CUDA_CHECK(cudaGetLastError());
+    }
+    prof_begin(GSR_PROF_PREPROCESS_BWD, s);
+    ewa_preprocess_bwd<<<(P + 255) / 256, 256, 0, s>>>(
+        P, a.D, a.M, a.means3D, a.scales, (const float4*)a.rotations, a.shs, a.cov3D_precomp, vc, focal_x, focal_y,
+        a.tan_fovx, a.tan_fovy, a.radii, gw.clamped, bw.gacc, a.dL_dmean2D, a.plane ? a.dL_dmean2D_abs : nullptr,
+        a.dL_dconic, a.dL_dopacity, a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D, a.shs ? a.dL_dsh : nullptr,
+        a.scales ? a.dL_dscale : nullptr, a.scales ? a.dL_drot : nullptr, a.plane ? a.dL_dall_map : nullptr);
+    prof_end(GSR_PROF_PREPROCESS_BWD, s);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    if (a.debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return GSR_OK;
+}
+}  // namespace gsr
+
+extern "C" {
+
+int gsr_gaussian_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer, gsr_buffer_fn imageBuffer,
+                         void* user, int P, int D, int M, const float* background, int width, int height,
+                         const float* means3D, const float* shs, const float* colors_precomp,
+                         const float* opacities, const float* scales, float scale_modifier,
+                         const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                         const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                         int prefiltered, float* out_color, int* radii, int debug, void* stream) {
+    const EwaFwdArgs a = {geometryBuffer, binningBuffer, imageBuffer, user, P, D, M, background, width, height, means3D, shs,
+                          colors_precomp, opacities, scales, scale_modifier, rotations, cov3D_precomp, nullptr, viewmatrix,
+                          projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color, radii, nullptr, nullptr, nullptr,
+                          false, false, debug, (cudaStream_t)stream};
+    return ewa_forward(a, "gsr_gaussian_forward");
+}
+
+int gsr_gaussian_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                          const float* means3D, const float* shs, const float* colors_precomp,
+                          const float* scales, float scale_modifier, const float* rotations,
+                          const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                          const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+                          char* geom_buffer, char* binning_buffer, char* image_buffer, const float* dL_dpix,
+                          float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                          float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                          int debug, void* stream) {
+    (void)colors_precomp;
+    const EwaBwdArgs a = {P, D, M, R, background, nullptr, width, height, means3D, shs, nullptr, scales, scale_modifier,
+                          rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, radii, geom_buffer,
+                          binning_buffer, image_buffer, dL_dpix, nullptr, nullptr, dL_dmean2D, nullptr, dL_dconic,
+                          dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, nullptr, false, false,
+                          debug, (cudaStream_t)stream};
+    return ewa_backward(a, "gsr_gaussian_backward");
+}
+
+int gsr_plane_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer, gsr_buffer_fn imageBuffer,
+                      void* user, int P, int D, int M, const float* background, int width, int height,
+                      const float* means3D, const float* shs, const float* colors_precomp,
+                      const float* opacities, const float* scales, float scale_modifier,
+                      const float* rotations, const float* cov3D_precomp, const float* all_map,
+                      const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                      float tan_fovy, int prefiltered, float* out_color, int* radii, int* out_observe,
+                      float* out_all_map, float* out_plane_depth, int render_geo, int debug, void* stream) {
+    const EwaFwdArgs a = {geometryBuffer, binningBuffer, imageBuffer, user, P, D, M, background, width, height, means3D, shs,
+                          colors_precomp, opacities, scales, scale_modifier, rotations, cov3D_precomp, all_map, viewmatrix,
+                          projmatrix, cam_pos, tan_fovx, tan_fovy, prefiltered, out_color, radii, out_observe, out_all_map,
+                          out_plane_depth, true, render_geo != 0, debug, (cudaStream_t)stream};
+    return ewa_forward(a, "gsr_plane_forward");
+}
+
+int gsr_plane_backward(int P, int D, int M, int R, const float* background, const float* all_map_pixels, int width,
+                       int height, const float* means3D, const float* shs, const float* colors_precomp,
+                       const float* all_maps, const float* scales, float scale_modifier, const float* rotations,
+                       const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                       const float* campos, float tan_fovx, float tan_fovy, const int* radii, char* geom_buffer,
+                       char* binning_buffer, char* image_buffer, const float* dL_dpix, const float* dL_dout_all_map,
+                       const float* dL_dout_plane_depth, float* dL_dmean2D, float* dL_dmean2D_abs, float* dL_dconic,
+                       float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                       float* dL_dscale, float* dL_drot, float* dL_dall_map, int render_geo, int debug, void* stream) {
+    (void)colors_precomp;
+    const EwaBwdArgs a = {P, D, M, R, background, all_map_pixels, width, height, means3D, shs, all_maps, scales,
+                          scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy,
+                          radii, geom_buffer, binning_buffer, image_buffer, dL_dpix, dL_dout_all_map, dL_dout_plane_depth,
+                          dL_dmean2D, dL_dmean2D_abs, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
+                          dL_dscale, dL_drot, dL_dall_map, true, render_geo != 0, debug, (cudaStream_t)stream};
+    return ewa_backward(a, "gsr_plane_backward");
+}
+
+int gsr_visible_filter(int P, int width, int height, const float* means3D, const float* scales, float scale_modifier,
+                       const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                       const float* projmatrix, float tan_fovx, float tan_fovy, int prefiltered, int* radii, int debug,
+                       void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P == 0) return GSR_OK;
+    if (P < 0 || width <= 0 || height <= 0 || !means3D || !viewmatrix || !projmatrix || !radii) {
+        set_error("gsr_visible_filter: invalid argument"); return GSR_E_INVALID;
+    }
+    if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr)) {
+        set_error("provide exactly one of scales+rotations / cov3D_precomp"); return GSR_E_INVALID;
+    }
+    const ViewParams vc = make_view(viewmatrix, projmatrix, nullptr, width, height, scale_modifier);
+    const float focal_y = (float)height / (2.0f * tan_fovy), focal_x = (float)width / (2.0f * tan_fovx);   // F/rasterizer_impl.cu:358-359
+    // prefiltered is honoured only in debug mode: it needs a flag word and a read-back, which the
+    // asynchronous product path avoids (the reference __trap()s inside the kernel)
+    (void)prefiltered; (void)debug;
+    ewa_preprocess_fwd<true><<<(P + 255) / 256, 256, 0, s>>>(
+        P, 0, 0, means3D, scales, (const float4*)rotations, nullptr, nullptr, cov3D_precomp, true, vc, focal_x, focal_y,
+        tan_fovx, tan_fovy, false, true, radii, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return GSR_OK;
 }
 

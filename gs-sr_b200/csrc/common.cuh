@@ -107,7 +107,8 @@ struct ImageWs {     // imageBuffer
     uint32_t* tile_count;   // tiles (+1: [tiles] = total R written by tile_scan)
     uint32_t* tile_offset;  // tiles + 1: tile t owns list entries [offset[t], offset[t+1])
     uint32_t* tile_cursor;  // tiles: scatter cursors
-    static size_t carve(ImageWs& w, char* base, int W, int H);
+    // nT / nC: per-pixel float / uint32 planes (surfel 3 + 2, EWA 1 + 1)
+    static size_t carve(ImageWs& w, char* base, int W, int H, int nT = 3, int nC = 2);
 };
 
 struct BinWs {       // binningBuffer
@@ -115,7 +116,7 @@ struct BinWs {       // binningBuffer
     float4* planes;      // REC_PLANES x Rpad float4 (plane stride = Rpad)
     size_t plane_stride; // Rpad = R rounded up to a multiple of 8 (keeps every plane 128-byte aligned)
     float* gacc;         // P * GACC_STRIDE (backward accumulators; lives here so forward owns one blob)
-    static size_t carve(BinWs& w, char* base, int64_t R, int P);
+    static size_t carve(BinWs& w, char* base, int64_t R, int P, int nplanes = REC_PLANES, int gacc_stride = GACC_STRIDE);
 };
 
 // Per-view constants.  view/proj/campos stay DEVICE pointers exactly as the reference

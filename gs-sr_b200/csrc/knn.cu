@@ -1,0 +1,407 @@
+// knn.cu -- distCUDA2: mean of the 3 smallest squared distances from every point to the other
+// points, for sm_100a.
+//
+// Result contract = reference SimpleKNN::knn (K/simple_knn.cu:186-221, boxMeanDist :132-184,
+// updateKBest :118-130): the EXACT 3 nearest neighbours (index-distinct; coincident points count
+// with distance 0), squared distances evaluated as fma(dz,dz, fma(dx,dx, dy*dy)) (the sequence
+// nvcc emits for the reference, read off its SASS), summed smallest-first and divided by 3.
+//
+// B200 design (not the reference's): the reference sorts by Morton code with CUB, cuts the order
+// into 1024-point boxes and lets EVERY point scan ALL boxes (O(P^2/1024) box tests, 2 host syncs,
+// cudaMalloc/thrust allocations per call).  Here:
+//   1. bounding box by ordered-uint atomics, 30-bit Morton codes;
+//   2. a hand-written stable LSD radix sort (4 passes x 8 bits: per-CTA digit histograms, one
+//      single-CTA scan, warp-match ranked scatter) -- no CUB, no temp allocation;
+//   3. an implicit 32-ary bounding-box hierarchy over the sorted order (leaf = 32 points = one
+//      warp-load, each parent = 32 children = one ballot);
+//   4. one WARP per leaf answers its 32 query points together: seed from the own leaf, then a
+//      warp-uniform depth-first walk that prunes a node when its box-to-box distance to the query
+//      leaf exceeds the warp's largest current 3rd-best distance; surviving leaves are loaded
+//      coalesced (one float4 per lane) and broadcast by shuffle.  No divergence, no per-thread
+//      stacks, everything asynchronous on the caller's stream.
+#include <cfloat>
+#include "common.cuh"
+#include "../../include/gsr_b200.h"
+
+namespace gsr {
+
+constexpr int KNN_LEAF = 32;                 // points per leaf, children per internal node
+constexpr int KNN_MAX_LEVELS = 8;            // 32^7 leaves > 2^31 points
+constexpr int RADIX_ITEMS = 8;               // keys per thread
+constexpr int RADIX_THREADS = 256;
+constexpr int RADIX_TILE = RADIX_ITEMS * RADIX_THREADS;
+constexpr uint32_t FULL = 0xffffffffu;
+
+struct KnnLevels {
+    int nlevels;                             // level 0 = leaves
+    int count[KNN_MAX_LEVELS];               // nodes per level
+    float4* box[KNN_MAX_LEVELS];             // 2 float4 per node: min.xyz, max.xyz
+};
+
+struct KnnWs {
+    uint32_t* bbox;      // [0..2] encoded min, [4..6] encoded max
+    uint32_t *keys0, *keys1, *vals0, *vals1;
+    uint32_t* hist;      // 256 x nblocks
+    float4* spts;        // sorted points: xyz + original index bits
+    KnnLevels lv;
+    static size_t carve(KnnWs& w, char* base, int P) {
+        Carver c(base);
+        const size_t n = P > 0 ? (size_t)P : 1;
+        const size_t nblocks = (n + RADIX_TILE - 1) / RADIX_TILE;
+        w.bbox = c.take<uint32_t>(8);
+        w.keys0 = c.take<uint32_t>(n); w.keys1 = c.take<uint32_t>(n);
+        w.vals0 = c.take<uint32_t>(n); w.vals1 = c.take<uint32_t>(n);
+        w.hist = c.take<uint32_t>(256 * nblocks + 1);
+        w.spts = c.take<float4>(n);
+        int cnt = (int)((n + KNN_LEAF - 1) / KNN_LEAF), l = 0;
+        for (;;) {
+            w.lv.count[l] = cnt;
+            w.lv.box[l] = c.take<float4>(2 * (size_t)cnt);
+            l++;
+            if (cnt <= KNN_LEAF || l == KNN_MAX_LEVELS) break;
+            cnt = (cnt + KNN_LEAF - 1) / KNN_LEAF;
+        }
+        w.lv.nlevels = l;
+        return c.used + 256;
+    }
+};
+
+// ---- 1. bounding box ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t enc_ordered(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void __launch_bounds__(256) knn_bbox(int P, const float* __restrict__ pts, uint32_t* __restrict__ bbox) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float v = __ldg(pts + 3 * (size_t)i + k);
+            mn[k] = fminf(mn[k], v);
+            mx[k] = fmaxf(mx[k], v);
+        }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(FULL, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(FULL, mx[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&bbox[k], enc_ordered(mn[k]));
+            atomicMax(&bbox[4 + k], enc_ordered(mx[k]));
+        }
+    }
+}
+
+// ---- 2. Morton codes (K/simple_knn.cu:46-75: 10 bits per axis) ---------------------------------------
+__device__ __forceinline__ uint32_t spread10(uint32_t x) {
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000FFu;
+    x = (x | (x << 8)) & 0x0300F00Fu;
+    x = (x | (x << 4)) & 0x030C30C3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+__global__ void __launch_bounds__(256) knn_morton(int P, const float* __restrict__ pts, const uint32_t* __restrict__ bbox,
+                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uint32_t code = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float lo = dec_ordered(bbox[k]), hi = dec_ordered(bbox[4 + k]);
+        const float ext = hi - lo;
+        const float t = ext > 0.f ? (__ldg(pts + 3 * (size_t)i + k) - lo) / ext : 0.f;
+        const uint32_t q = (uint32_t)fminf(fmaxf(t * 1023.0f, 0.f), 1023.f);   // NaN -> 0
+        code |= spread10(q) << k;
+    }
+    keys[i] = code;
+    vals[i] = (uint32_t)i;
+}
+
+// ---- 3. stable LSD radix sort, 8 bits per pass --------------------------------------------------------
+__global__ void __launch_bounds__(RADIX_THREADS) radix_hist(int n, const uint32_t* __restrict__ keys, int shift,
+                                                            uint32_t* __restrict__ hist, int nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * RADIX_TILE;
+#pragma unroll
+    for (int k = 0; k < RADIX_ITEMS; k++) {
+        const int i = base + k * RADIX_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of m counters in place (single CTA; digit-major layout makes it the global offset table)
+__global__ void __launch_bounds__(1024) radix_scan(int m, uint32_t* __restrict__ data) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < m ? data[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane], s = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sums[lane] = s - w;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sums[warp] + (x - v);
+        if (i < m) data[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+// Each warp owns a contiguous 256-key slice of the CTA's tile and walks it 32 keys at a time, so
+// (warp, round, lane) order == input order: ranks from __match_any_sync keep the sort stable.
+__global__ void __launch_bounds__(RADIX_THREADS) radix_scatter(int n, const uint32_t* __restrict__ keys_in,
+                                                               const uint32_t* __restrict__ vals_in, int shift,
+                                                               const uint32_t* __restrict__ offsets, int nblocks,
+                                                               uint32_t* __restrict__ keys_out,
+                                                               uint32_t* __restrict__ vals_out) {
+    constexpr int NW = RADIX_THREADS / 32;
+    __shared__ uint32_t cnt[NW][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NW * 256; i += RADIX_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int wbase = blockIdx.x * RADIX_TILE + warp * (RADIX_TILE / NW);
+    uint32_t k[RADIX_ITEMS], v[RADIX_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        const int i = wbase + r * 32 + lane;
+        k[r] = i < n ? keys_in[i] : 0xffffffffu;
+        v[r] = i < n ? vals_in[i] : 0u;
+        if (i < n) atomicAdd(&cnt[warp][(k[r] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    {   // per digit: exclusive prefix over warps, plus the tile's global base
+        const int d = threadIdx.x;
+        uint32_t run = offsets[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const uint32_t c = cnt[w][d];
+            cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        const int i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = ok ? ((k[r] >> shift) & 255u) : 256u + (uint32_t)lane;   // inactive lanes match nobody
+        const uint32_t peers = __match_any_sync(FULL, d);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t pos = 0;
+        if (ok) {
+            pos = cnt[warp][d] + rank;
+            keys_out[pos] = k[r];
+            vals_out[pos] = v[r];
+        }
+        __syncwarp();
+        if (ok && rank == 0) cnt[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+}
+
+// ---- 4. gather points into sorted order, 5. box hierarchy -----------------------------------------------
+__global__ void __launch_bounds__(256) knn_gather(int P, const float* __restrict__ pts, const uint32_t* __restrict__ order,
+                                                  float4* __restrict__ spts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const uint32_t o = order[i];
+    spts[i] = make_float4(__ldg(pts + 3 * (size_t)o), __ldg(pts + 3 * (size_t)o + 1), __ldg(pts + 3 * (size_t)o + 2),
+                          __uint_as_float(o));
+}
+
+// one warp per parent: bounding box of its (up to) 32 children; level 0 children are points
+__global__ void __launch_bounds__(256) knn_build_level(int nchildren, const float4* __restrict__ child, bool child_is_point,
+                                                       int nparents, float4* __restrict__ parent) {
+    const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (node >= nparents) return;
+    const int c = node * KNN_LEAF + lane;
+    float3 mn = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), mx = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    if (c < nchildren) {
+        if (child_is_point) {
+            const float4 p = child[c];
+            mn = mx = make_float3(p.x, p.y, p.z);
+        } else {
+            const float4 a = child[2 * (size_t)c], b = child[2 * (size_t)c + 1];
+            mn = make_float3(a.x, a.y, a.z);
+            mx = make_float3(b.x, b.y, b.z);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn.x = fminf(mn.x, __shfl_xor_sync(FULL, mn.x, o)); mn.y = fminf(mn.y, __shfl_xor_sync(FULL, mn.y, o));
+        mn.z = fminf(mn.z, __shfl_xor_sync(FULL, mn.z, o));
+        mx.x = fmaxf(mx.x, __shfl_xor_sync(FULL, mx.x, o)); mx.y = fmaxf(mx.y, __shfl_xor_sync(FULL, mx.y, o));
+        mx.z = fmaxf(mx.z, __shfl_xor_sync(FULL, mx.z, o));
+    }
+    if (lane == 0) {
+        parent[2 * (size_t)node] = make_float4(mn.x, mn.y, mn.z, 0.f);
+        parent[2 * (size_t)node + 1] = make_float4(mx.x, mx.y, mx.z, 0.f);
+    }
+}
+
+// ---- 6. query ------------------------------------------------------------------------------------------
+// updateKBest<3>, K/simple_knn.cu:118-130, with the reference build's rounding of the distance
+__device__ __forceinline__ void update3(float3 ref, float4 q, float& b0, float& b1, float& b2) {
+    const float dx = q.x - ref.x, dy = q.y - ref.y, dz = q.z - ref.z;
+    float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    if (b0 > d) { const float t = b0; b0 = d; d = t; }
+    if (b1 > d) { const float t = b1; b1 = d; d = t; }
+    if (b2 > d) b2 = d;
+}
+// squared gap between two boxes, deflated a little so that rounding can never prune a box holding a
+// point at exactly the current bound
+__device__ __forceinline__ float box_gap2(float3 amin, float3 amax, float4 bmin, float4 bmax) {
+    const float gx = fmaxf(fmaxf(bmin.x - amax.x, amin.x - bmax.x), 0.f);
+    const float gy = fmaxf(fmaxf(bmin.y - amax.y, amin.y - bmax.y), 0.f);
+    const float gz = fmaxf(fmaxf(bmin.z - amax.z, amin.z - bmax.z), 0.f);
+    return (gx * gx + gy * gy + gz * gz) * 0.9999f;
+}
+
+__global__ void __launch_bounds__(256) knn_query(int P, const float4* __restrict__ spts, const KnnLevels lv,
+                                                 float* __restrict__ out) {
+    const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (leaf >= lv.count[0]) return;
+    const int me = leaf * KNN_LEAF + lane;
+    const bool have = me < P;
+    const float4 self = have ? spts[me] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float3 ref = make_float3(self.x, self.y, self.z);
+    float b0 = FLT_MAX, b1 = FLT_MAX, b2 = FLT_MAX;
+    const int nmine = min(KNN_LEAF, P - leaf * KNN_LEAF);
+    // seed: the other points of the own leaf
+    for (int k = 0; k < nmine; k++) {
+        float4 q;
+        q.x = __shfl_sync(FULL, self.x, k); q.y = __shfl_sync(FULL, self.y, k); q.z = __shfl_sync(FULL, self.z, k);
+        if (k != lane) update3(ref, q, b0, b1, b2);
+    }
+    const float4 abmin = lv.box[0][2 * (size_t)leaf], abmax = lv.box[0][2 * (size_t)leaf + 1];
+    const float3 amin = make_float3(abmin.x, abmin.y, abmin.z), amax = make_float3(abmax.x, abmax.y, abmax.z);
+    // warp bound: largest 3rd-best among the lanes that hold a query point
+    float bound = __uint_as_float(__reduce_max_sync(FULL, have ? __float_as_uint(b2) : 0u));
+
+    // warp-uniform depth-first walk; entry = (level of the children, first child index, pending mask)
+    int st_level[KNN_MAX_LEVELS], st_first[KNN_MAX_LEVELS];
+    uint32_t st_mask[KNN_MAX_LEVELS];
+    int sp = 0;
+    {
+        const int top = lv.nlevels - 1;
+        bool pass = false;
+        if (lane < lv.count[top]) {
+            const float4 mn = lv.box[top][2 * (size_t)lane], mx = lv.box[top][2 * (size_t)lane + 1];
+            pass = !(box_gap2(amin, amax, mn, mx) > bound);
+        }
+        st_level[0] = top; st_first[0] = 0; st_mask[0] = __ballot_sync(FULL, pass);
+        sp = 1;
+    }
+    while (sp > 0) {
+        uint32_t& mask = st_mask[sp - 1];
+        if (mask == 0u) { sp--; continue; }
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int level = st_level[sp - 1];
+        const int node = st_first[sp - 1] + bit;
+        // the bound may have shrunk since this node was queued: test again (one broadcast load)
+        {
+            const float4 mn = lv.box[level][2 * (size_t)node], mx = lv.box[level][2 * (size_t)node + 1];
+            if (box_gap2(amin, amax, mn, mx) > bound) continue;
+        }
+        if (level == 0) {
+            if (node == leaf) continue;   // seeded above
+            const int first = node * KNN_LEAF;
+            const int cnt = min(KNN_LEAF, P - first);
+            const float4 mine = (lane < cnt) ? spts[first + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < cnt; k++) {
+                float4 q;
+                q.x = __shfl_sync(FULL, mine.x, k); q.y = __shfl_sync(FULL, mine.y, k); q.z = __shfl_sync(FULL, mine.z, k);
+                update3(ref, q, b0, b1, b2);
+            }
+            bound = __uint_as_float(__reduce_max_sync(FULL, have ? __float_as_uint(b2) : 0u));
+        } else {
+            const int cl = level - 1, first = node * KNN_LEAF;
+            const int c = first + lane;
+            bool pass = false;
+            if (c < lv.count[cl]) {
+                const float4 mn = lv.box[cl][2 * (size_t)c], mx = lv.box[cl][2 * (size_t)c + 1];
+                pass = !(box_gap2(amin, amax, mn, mx) > bound);
+            }
+            const uint32_t m = __ballot_sync(FULL, pass);
+            if (m != 0u) { st_level[sp] = cl; st_first[sp] = first; st_mask[sp] = m; sp++; }
+        }
+    }
+    if (have) out[__float_as_uint(self.w)] = __fdiv_rn(__fadd_rn(__fadd_rn(b0, b1), b2), 3.0f);
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+size_t gsr_dist2_knn3_workspace(int P) {
+    KnnWs w;
+    return KnnWs::carve(w, nullptr, P < 0 ? 0 : P) + 256;
+}
+
+int gsr_dist2_knn3(int P, const float* points, float* meanDists, void* workspace, void* stream_v) {
+    cudaStream_t s = (cudaStream_t)stream_v;
+    if (P == 0) return GSR_OK;
+    if (P < 0 || !points || !meanDists || !workspace) { set_error("gsr_dist2_knn3: invalid argument"); return GSR_E_INVALID; }
+    KnnWs w;
+    char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    KnnWs::carve(w, base, P);
+    GSR_CUDA_CHECK(cudaMemsetAsync(w.bbox, 0xff, 4 * sizeof(uint32_t), s));
+    GSR_CUDA_CHECK(cudaMemsetAsync(w.bbox + 4, 0, 4 * sizeof(uint32_t), s));
+    const int nb256 = (P + 255) / 256;
+    knn_bbox<<<min(nb256, 148 * 8), 256, 0, s>>>(P, points, w.bbox);
+    knn_morton<<<nb256, 256, 0, s>>>(P, points, w.bbox, w.keys0, w.vals0);
+    const int nblocks = (P + RADIX_TILE - 1) / RADIX_TILE;
+    uint32_t *ki = w.keys0, *vi = w.vals0, *ko = w.keys1, *vo = w.vals1;
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 8 * pass;
+        radix_hist<<<nblocks, RADIX_THREADS, 0, s>>>(P, ki, shift, w.hist, nblocks);
+        radix_scan<<<1, 1024, 0, s>>>(256 * nblocks, w.hist);
+        radix_scatter<<<nblocks, RADIX_THREADS, 0, s>>>(P, ki, vi, shift, w.hist, nblocks, ko, vo);
+        uint32_t* t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+    }
+    knn_gather<<<nb256, 256, 0, s>>>(P, points, vi, w.spts);
+    for (int l = 0; l < w.lv.nlevels; l++) {
+        const int nparents = w.lv.count[l];
+        const int nchildren = l == 0 ? P : w.lv.count[l - 1];
+        knn_build_level<<<(nparents * 32 + 255) / 256, 256, 0, s>>>(nchildren, l == 0 ? w.spts : w.lv.box[l - 1], l == 0,
+                                                                   nparents, w.lv.box[l]);
+    }
+    knn_query<<<(w.lv.count[0] * 32 + 255) / 256, 256, 0, s>>>(P, w.spts, w.lv, meanDists);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    return GSR_OK;
+}
+
+}  // extern "C"

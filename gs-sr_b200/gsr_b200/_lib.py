@@ -40,6 +40,28 @@ def lib():
         + [_fp] * 15 + [C.c_int, C.c_void_p])
     L.gsr_mark_visible.restype = C.c_int
     L.gsr_mark_visible.argtypes = [C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]
+    head = [BUFFER_FN, BUFFER_FN, BUFFER_FN, C.c_void_p, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int]
+    L.gsr_gaussian_forward.restype = C.c_int
+    L.gsr_gaussian_forward.argtypes = (head + [_fp] * 5 + [C.c_float] + [_fp] * 5 + [C.c_float, C.c_float, C.c_int]
+                                       + [_fp] * 2 + [C.c_int, C.c_void_p])
+    L.gsr_gaussian_backward.restype = C.c_int
+    L.gsr_gaussian_backward.argtypes = (
+        [C.c_int] * 4 + [_fp, C.c_int, C.c_int] + [_fp] * 4 + [C.c_float] + [_fp] * 5 + [C.c_float, C.c_float]
+        + [_fp] * 14 + [C.c_int, C.c_void_p])
+    L.gsr_plane_forward.restype = C.c_int
+    L.gsr_plane_forward.argtypes = (head + [_fp] * 5 + [C.c_float] + [_fp] * 6 + [C.c_float, C.c_float, C.c_int]
+                                    + [_fp] * 5 + [C.c_int, C.c_int, C.c_void_p])
+    L.gsr_plane_backward.restype = C.c_int
+    L.gsr_plane_backward.argtypes = (
+        [C.c_int] * 4 + [_fp, _fp, C.c_int, C.c_int] + [_fp] * 5 + [C.c_float] + [_fp] * 5 + [C.c_float, C.c_float]
+        + [_fp] * 18 + [C.c_int, C.c_int, C.c_void_p])
+    L.gsr_visible_filter.restype = C.c_int
+    L.gsr_visible_filter.argtypes = ([C.c_int] * 3 + [_fp, _fp, C.c_float] + [_fp] * 4 + [C.c_float, C.c_float, C.c_int, _fp,
+                                                                                    C.c_int, C.c_void_p])
+    L.gsr_dist2_knn3_workspace.restype = C.c_size_t
+    L.gsr_dist2_knn3_workspace.argtypes = [C.c_int]
+    L.gsr_dist2_knn3.restype = C.c_int
+    L.gsr_dist2_knn3.argtypes = [C.c_int, _fp, _fp, _fp, C.c_void_p]
     _LIB = L
     return L
 

@@ -123,6 +123,103 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
 int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);
 
+
+/* ---- 3DGS rasterizer: diff_gaussian_rasterization -------------------------- */
+
+/* Replaces CudaRasterizer::Rasterizer::forward
+ * (G/cuda_rasterizer/rasterizer.h:31-53, G/cuda_rasterizer/rasterizer_impl.cu:198-337)
+ * as called from RasterizeGaussiansCUDA (G/rasterize_points.cu:35-113).
+ *   out_color (3,H,W) and radii (P) are fully written.  Exactly one of shs /
+ *   colors_precomp and one of (scales+rotations) / cov3D_precomp must be non-NULL;
+ *   scales is (P,3) packed, cov3D_precomp (P,6) upper-triangular.
+ * Returns num_rendered. */
+int gsr_gaussian_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer,
+                         gsr_buffer_fn imageBuffer, void* user,
+                         int P, int D, int M, const float* background, int width, int height,
+                         const float* means3D, const float* shs, const float* colors_precomp,
+                         const float* opacities, const float* scales, float scale_modifier,
+                         const float* rotations, const float* cov3D_precomp,
+                         const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                         float tan_fovx, float tan_fovy, int prefiltered,
+                         float* out_color, int* radii, int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::backward
+ * (G/cuda_rasterizer/rasterizer.h:55-85, G/cuda_rasterizer/rasterizer_impl.cu:341-433)
+ * as called from RasterizeGaussiansBackwardCUDA (G/rasterize_points.cu:115-197).
+ * All dL_* outputs are fully written; dL_dconic (P,4: x, y, 0, w) is scratch the
+ * reference also exposes at this level and may be NULL, as may dL_dsh (M == 0),
+ * dL_dscale and dL_drot (cov3D_precomp given). */
+int gsr_gaussian_backward(int P, int D, int M, int R, const float* background, int width, int height,
+                          const float* means3D, const float* shs, const float* colors_precomp,
+                          const float* scales, float scale_modifier, const float* rotations,
+                          const float* cov3D_precomp, const float* viewmatrix,
+                          const float* projmatrix, const float* campos, float tan_fovx,
+                          float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+                          char* image_buffer, const float* dL_dpix, float* dL_dmean2D,
+                          float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                          float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                          int debug, void* stream);
+
+/* ---- PGSR plane rasterizer: diff_plane_rasterization ------------------------ */
+
+/* Replaces CudaRasterizer::Rasterizer::forward
+ * (L/cuda_rasterizer/rasterizer.h:31-61, L/cuda_rasterizer/rasterizer_impl.cu:200-352)
+ * as called from RasterizeGaussiansCUDA (L/rasterize_points.cu:35-125).
+ *   all_map (P,5) may be NULL when render_geo == 0.  out_observe (P) int32 is fully
+ *   written (count of pixels on which the Gaussian was blended with T > 0.5);
+ *   out_all_map (5,H,W) and out_plane_depth (1,H,W) are written when render_geo != 0
+ *   and zero-filled otherwise. */
+int gsr_plane_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer,
+                      gsr_buffer_fn imageBuffer, void* user,
+                      int P, int D, int M, const float* background, int width, int height,
+                      const float* means3D, const float* shs, const float* colors_precomp,
+                      const float* opacities, const float* scales, float scale_modifier,
+                      const float* rotations, const float* cov3D_precomp, const float* all_map,
+                      const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                      float tan_fovx, float tan_fovy, int prefiltered,
+                      float* out_color, int* radii, int* out_observe, float* out_all_map,
+                      float* out_plane_depth, int render_geo, int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::backward
+ * (L/cuda_rasterizer/rasterizer.h:63-99, L/cuda_rasterizer/rasterizer_impl.cu:356-462)
+ * as called from RasterizeGaussiansBackwardCUDA (L/rasterize_points.cu:127-231).
+ * all_map_pixels = the forward's out_all_map.  dL_dmean2D_abs (P,3) and dL_dall_map
+ * (P,5) are fully written (zeros when render_geo == 0 for the latter). */
+int gsr_plane_backward(int P, int D, int M, int R, const float* background,
+                       const float* all_map_pixels, int width, int height,
+                       const float* means3D, const float* shs, const float* colors_precomp,
+                       const float* all_maps, const float* scales, float scale_modifier,
+                       const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                       const float* projmatrix, const float* campos, float tan_fovx,
+                       float tan_fovy, const int* radii, char* geom_buffer, char* binning_buffer,
+                       char* image_buffer, const float* dL_dpix, const float* dL_dout_all_map,
+                       const float* dL_dout_plane_depth, float* dL_dmean2D, float* dL_dmean2D_abs,
+                       float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                       float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                       float* dL_dall_map, int render_geo, int debug, void* stream);
+
+/* ---- scaffold_filter ------------------------------------------------------------ */
+
+/* Replaces CudaRasterizer::Rasterizer::visible_filter
+ * (F/cuda_rasterizer/rasterizer.h:56-72, F/cuda_rasterizer/rasterizer_impl.cu:340-396)
+ * as called from RasterizeGaussiansfilterCUDA (F/rasterize_points.cu:220-284).
+ * radii (P) int32 is fully written; needs no scratch (the reference still resizes
+ * its geometry and image chunks). */
+int gsr_visible_filter(int P, int width, int height, const float* means3D, const float* scales,
+                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                       const float* viewmatrix, const float* projmatrix, float tan_fovx,
+                       float tan_fovy, int prefiltered, int* radii, int debug, void* stream);
+
+/* ---- simple_knn ---------------------------------------------------------------------- */
+
+/* Replaces SimpleKNN::knn (K/simple_knn.h:15-19, K/simple_knn.cu:186-221) as called from
+ * distCUDA2 (K/spatial.cu:14-25): meanDists[i] = mean of the 3 smallest squared
+ * distances from points[i] to the other points.  `workspace` must hold
+ * gsr_dist2_knn3_workspace(P) bytes of device memory (the reference cudaMallocs /
+ * thrust-allocates per call and synchronises twice; this call is fully asynchronous). */
+size_t gsr_dist2_knn3_workspace(int P);
+int gsr_dist2_knn3(int P, const float* points, float* meanDists, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
