@@ -106,3 +106,43 @@ def test_synthetic_scene_is_deterministic():
     assert np.allclose(np.linalg.norm(a.rotations, axis=1), 1, atol=1e-6)
     # full_proj = view @ proj and proj[3,2] == 1 (clip w = view z), cameras/__init__.py:85-88
     assert abs(a.cam.projmatrix[2, 3] - 1.0) < 1e-6
+
+
+def test_ewa_modules_mirror_reference_api():
+    """diff_gaussian_rasterization / diff_plane_rasterization / scaffold_filter / simple_knn._C surface."""
+    import diff_gaussian_rasterization as dgr
+    import diff_plane_rasterization as dpr
+    import scaffold_filter as sf
+    from simple_knn._C import distCUDA2
+    base = ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+            "sh_degree", "campos", "prefiltered")
+    assert dgr.GaussianRasterizationSettings._fields == base + ("debug",)          # G/...__init__.py:157-169
+    assert dpr.GaussianRasterizationSettings._fields == base + ("render_geo", "debug")   # L/...__init__.py:173-186
+    assert sf.GaussianRasterizationSettings._fields == base + ("debug",)           # F/...__init__.py:160-172
+    z = torch.zeros(3)
+    m = torch.zeros(4, 3)
+    rg = dgr.GaussianRasterizer(dgr.GaussianRasterizationSettings(8, 8, 1.0, 1.0, z, 1.0, torch.eye(4), torch.eye(4), 0, z, False, False))
+    rp = dpr.GaussianRasterizer(dpr.GaussianRasterizationSettings(8, 8, 1.0, 1.0, z, 1.0, torch.eye(4), torch.eye(4), 0, z, False, True, False))
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        rg(means3D=m, means2D=m, opacities=torch.zeros(4, 1), scales=m, rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed"):
+        rp(means3D=m, means2D=m, means2D_abs=m, opacities=torch.zeros(4, 1), colors_precomp=m)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        rg(means3D=m, means2D=m, opacities=torch.zeros(4, 1), colors_precomp=m, scales=m, rotations=torch.zeros(4, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        rp(means3D=m, means2D=m, means2D_abs=m, opacities=torch.zeros(4, 1), colors_precomp=m, scales=m,
+           rotations=torch.zeros(4, 4), all_map=torch.zeros(4, 5))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        sf.GaussianRasterizer(sf.GaussianRasterizationSettings(8, 8, 1.0, 1.0, z, 1.0, torch.eye(4), torch.eye(4), 0, z, False, False)).visible_filter(m, m, torch.zeros(4, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        distCUDA2(m)
+
+
+def test_ewa_entry_points_reject_bad_arguments_without_gpu():
+    import gsr_b200
+    L = gsr_b200.lib()
+    assert L.gsr_visible_filter(5, 8, 8, None, None, 1.0, None, None, None, None, 1.0, 1.0, 0, None, 0, None) == -1
+    assert L.gsr_dist2_knn3(5, None, None, None, None) == -1
+    assert L.gsr_dist2_knn3(0, None, None, None, None) == 0
+    assert L.gsr_dist2_knn3_workspace(1000) > 1000 * 16
+    assert L.gsr_gaussian_backward(0, *([0] * 3), None, 0, 0, *([None] * 4), 1.0, *([None] * 5), 1.0, 1.0, *([None] * 14), 0, None) == 0
