@@ -1,0 +1,176 @@
+// tsdf.cu -- multi-view TSDF / colour fusion of rendered depth + RGB maps on a set of sample
+// points (the voxel lattice that GS-SR hands to marching cubes), for sm_100a.
+//
+// Result contract = GaussianExtractor.extract_mesh_unbounded's in-repo torch rule
+// (/root/reference/gssr/utils/mesh_utils.py):
+//   contract / uncontract                :187-193
+//   compute_sdf_perframe                 :195-207  project with full_proj_transform (row-vector),
+//                                                  mask_proj = |ndc.xy| < 1 & z > 0, bilinear grid_sample
+//                                                  (border padding, align_corners=True) of depth and RGB,
+//                                                  sdf = depth - z
+//   compute_unbounded_tsdf               :209-246  adaptive truncation 5*voxel/(2 - min(|x|,1.9)) outside
+//                                                  the unit ball, running mean
+//                                                  tsdf <- (tsdf*w + clamp(sdf/trunc,-1,1))/(w+1) (same for
+//                                                  RGB) over the views with sdf > -trunc, w0 = 1, tsdf0 = 1
+// The reference runs ~25 full-array torch passes PER VIEW over the 16.7 M-point chunk
+// (cat, matmul, divide, masks, two grid_samples, masked gathers/scatters of tsdf / rgb / weights).
+//
+// B200 design: ONE pass over the samples for ALL views.  One thread owns one sample (consecutive
+// threads = consecutive lattice points along the fastest axis, so a warp's projections fall on
+// neighbouring pixels and its 4-tap gathers hit the same few 128-byte lines); tsdf, weight and RGB
+// stay in registers across the view loop and are written once; the per-view constants (projection,
+// image size, map pointers: 96 bytes) are staged 64 views at a time into shared memory and read as
+// warp-uniform broadcasts; depth / RGB maps are read through the read-only path and live in the
+// 126 MB L2 (6.8 MB per 1600x1060 depth map).  HBM traffic per sample: 12 B in, 4 (+12) B out,
+// independent of the number of views.
+#include "common.cuh"
+#include "../../include/gsr_b200.h"
+
+namespace gsr {
+
+constexpr int TSDF_VCHUNK = 64;
+constexpr int TSDF_THREADS = 256;
+
+struct __align__(16) TsdfViewDev {
+    float m[16];          // full_proj_transform, row-major (4,4), row-vector convention: clip = [x y z 1] @ M
+    int W, H;
+    int pad0, pad1;
+    const float* depth;   // (H, W)
+    const float* rgb;     // (3, H, W) or NULL
+};
+static_assert(sizeof(TsdfViewDev) == 96, "TsdfViewDev must stay 96 bytes (matches gsr_tsdf_view)");
+
+// torch grid_sample, bilinear, padding_mode='border', align_corners=True
+// (aten/src/ATen/native/cuda/GridSampler.cuh: grid_sampler_unnormalize, clip_coordinates).
+struct BilinearTaps {
+    int x0, y0, x1, y1;
+    float nw, ne, sw, se;
+    bool x1_in, y1_in;
+};
+
+__device__ __forceinline__ BilinearTaps bilinear_taps(float gx, float gy, int W, int H) {
+    BilinearTaps t;
+    float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
+    float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
+    ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    t.x0 = (int)fx0; t.y0 = (int)fy0; t.x1 = t.x0 + 1; t.y1 = t.y0 + 1;
+    const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+    t.nw = (fx1 - ix) * (fy1 - iy);
+    t.ne = (ix - fx0) * (fy1 - iy);
+    t.sw = (fx1 - ix) * (iy - fy0);
+    t.se = (ix - fx0) * (iy - fy0);
+    t.x1_in = t.x1 < W;
+    t.y1_in = t.y1 < H;
+    return t;
+}
+
+__device__ __forceinline__ float sample_plane(const float* __restrict__ img, int W, const BilinearTaps& t) {
+    const float* r0 = img + (size_t)t.y0 * W;
+    float out = __ldg(r0 + t.x0) * t.nw;
+    if (t.x1_in) out += __ldg(r0 + t.x1) * t.ne;
+    if (t.y1_in) {
+        const float* r1 = r0 + W;
+        out += __ldg(r1 + t.x0) * t.sw;
+        if (t.x1_in) out += __ldg(r1 + t.x1) * t.se;
+    }
+    return out;
+}
+
+template <bool RGB>
+__global__ void __launch_bounds__(TSDF_THREADS)
+tsdf_fuse_kernel(long long n, const float* __restrict__ samples, int contracted, float cx, float cy, float cz,
+                 float radius, float voxel_size, int nviews, const TsdfViewDev* __restrict__ views, int init,
+                 float* __restrict__ tsdf_io, float* __restrict__ weight_io, float* __restrict__ rgb_io) {
+    __shared__ TsdfViewDev sviews[TSDF_VCHUNK];
+    const long long i = (long long)blockIdx.x * TSDF_THREADS + threadIdx.x;
+    const bool live = i < n;
+
+    float x = 0.f, y = 0.f, z = 0.f, trunc = 5.f * voxel_size;
+    float tsdf = 1.f, w = 1.f, r = 0.f, g = 0.f, b = 0.f;
+    if (live) {
+        x = samples[3 * i]; y = samples[3 * i + 1]; z = samples[3 * i + 2];
+        if (contracted) {
+            // mesh_utils.py:215-219 (adaptive truncation) and :190-193, :248-250 (uncontract, unnormalize)
+            const float mag = sqrtf(x * x + y * y + z * z);
+            if (mag > 1.f) trunc *= 1.f / (2.f - fminf(mag, 1.9f));
+            if (!(mag < 1.f)) {
+                const float s = 1.f / (2.f - mag);
+                x = s * (x / mag); y = s * (y / mag); z = s * (z / mag);
+            }
+            x = x * radius + cx; y = y * radius + cy; z = z * radius + cz;
+        }
+        if (!init) {
+            tsdf = tsdf_io[i]; w = weight_io[i];
+            if (RGB) { r = rgb_io[3 * i]; g = rgb_io[3 * i + 1]; b = rgb_io[3 * i + 2]; }
+        }
+    }
+
+    for (int v0 = 0; v0 < nviews; v0 += TSDF_VCHUNK) {
+        const int nv = min(TSDF_VCHUNK, nviews - v0);
+        __syncthreads();
+        {   // stage nv view descriptors (96 B each = 6 x 16 B) with coalesced 128-bit copies
+            const float4* src = reinterpret_cast<const float4*>(views + v0);
+            float4* dst = reinterpret_cast<float4*>(sviews);
+            for (int k = threadIdx.x; k < nv * 6; k += TSDF_THREADS) dst[k] = __ldg(src + k);
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int v = 0; v < nv; v++) {
+            const TsdfViewDev& V = sviews[v];
+            const float hx = x * V.m[0] + y * V.m[4] + z * V.m[8] + V.m[12];
+            const float hy = x * V.m[1] + y * V.m[5] + z * V.m[9] + V.m[13];
+            const float hw = x * V.m[3] + y * V.m[7] + z * V.m[11] + V.m[15];
+            const float u = hx / hw, t = hy / hw;
+            const bool mask_proj = (u > -1.f) && (u < 1.f) && (t > -1.f) && (t < 1.f) && (hw > 0.f);
+            if (!mask_proj) continue;
+            const BilinearTaps taps = bilinear_taps(u, t, V.W, V.H);
+            const float sdf = sample_plane(V.depth, V.W, taps) - hw;
+            if (!(sdf > -trunc)) continue;
+            const float s = fminf(fmaxf(sdf / trunc, -1.f), 1.f);
+            const float wp = w + 1.f;
+            tsdf = (tsdf * w + s) / wp;
+            if (RGB) {
+                const size_t plane = (size_t)V.W * V.H;
+                r = (r * w + sample_plane(V.rgb, V.W, taps)) / wp;
+                g = (g * w + sample_plane(V.rgb + plane, V.W, taps)) / wp;
+                b = (b * w + sample_plane(V.rgb + 2 * plane, V.W, taps)) / wp;
+            }
+            w = wp;
+        }
+    }
+    if (live) {
+        tsdf_io[i] = tsdf;
+        if (weight_io) weight_io[i] = w;
+        if (RGB) { rgb_io[3 * i] = r; rgb_io[3 * i + 1] = g; rgb_io[3 * i + 2] = b; }
+    }
+}
+
+}  // namespace gsr
+
+extern "C" int gsr_tsdf_fuse(long long n, const float* samples, int contracted, const float* center, float radius,
+                             float voxel_size, int nviews, const gsr_tsdf_view* views, int init, float* tsdf,
+                             float* weights, float* rgb, void* stream_v) {
+    using namespace gsr;
+    static_assert(sizeof(gsr_tsdf_view) == sizeof(TsdfViewDev), "gsr_tsdf_view layout");
+    cudaStream_t s = (cudaStream_t)stream_v;
+    if (n < 0 || nviews < 0 || (n > 0 && (!samples || !tsdf)) || (nviews > 0 && !views) || !(voxel_size > 0.f) ||
+        (contracted && !(radius > 0.f)) || (!init && !weights)) {
+        set_error("gsr_tsdf_fuse: invalid argument");
+        return GSR_E_INVALID;
+    }
+    if (n == 0) return GSR_OK;
+    const float cx = center ? center[0] : 0.f, cy = center ? center[1] : 0.f, cz = center ? center[2] : 0.f;
+    const long long blocks = (n + TSDF_THREADS - 1) / TSDF_THREADS;
+    if (blocks > 0x7fffffffLL) { set_error("gsr_tsdf_fuse: too many samples (%lld)", n); return GSR_E_OVERFLOW; }
+    const TsdfViewDev* vd = reinterpret_cast<const TsdfViewDev*>(views);
+    if (rgb)
+        tsdf_fuse_kernel<true><<<(unsigned)blocks, TSDF_THREADS, 0, s>>>(n, samples, contracted, cx, cy, cz, radius,
+                                                                         voxel_size, nviews, vd, init, tsdf, weights, rgb);
+    else
+        tsdf_fuse_kernel<false><<<(unsigned)blocks, TSDF_THREADS, 0, s>>>(n, samples, contracted, cx, cy, cz, radius,
+                                                                          voxel_size, nviews, vd, init, tsdf, weights, nullptr);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    return GSR_OK;
+}

@@ -62,6 +62,9 @@ def lib():
     L.gsr_dist2_knn3_workspace.argtypes = [C.c_int]
     L.gsr_dist2_knn3.restype = C.c_int
     L.gsr_dist2_knn3.argtypes = [C.c_int, _fp, _fp, _fp, C.c_void_p]
+    L.gsr_tsdf_fuse.restype = C.c_int
+    L.gsr_tsdf_fuse.argtypes = [C.c_longlong, _fp, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, _fp,
+                                C.c_int, _fp, _fp, _fp, C.c_void_p]
     _LIB = L
     return L
 

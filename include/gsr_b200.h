@@ -220,6 +220,36 @@ int gsr_visible_filter(int P, int width, int height, const float* means3D, const
 size_t gsr_dist2_knn3_workspace(int P);
 int gsr_dist2_knn3(int P, const float* points, float* meanDists, void* workspace, void* stream);
 
+/* ---- TSDF fusion (mesh extraction) --------------------------------------------------- */
+
+/* One view of the fusion: the camera's full_proj_transform ((4,4) row-major, row-vector
+ * convention: clip = [x y z 1] @ M, gssr/cameras/__init__.py:85-88) and its rendered maps
+ * (device pointers; depth (H,W), rgb (3,H,W) or NULL when colours are not requested). 96 bytes. */
+typedef struct gsr_tsdf_view {
+    float full_proj[16];
+    int width, height;
+    int reserved0, reserved1;
+    const float* depth;
+    const float* rgb;
+} gsr_tsdf_view;
+
+/* Replaces the per-view torch loop of GaussianExtractor.extract_mesh_unbounded
+ * (gssr/utils/mesh_utils.py:195-246: compute_sdf_perframe + compute_unbounded_tsdf), the
+ * function GS-SR hands to marching cubes as `sdf` (:254, gssr/utils/mcube_utils.py:57-68) and
+ * uses to colour the mesh vertices (:275).  For every sample point i (samples (n,3)):
+ *   contracted != 0: truncation 5*voxel_size/(2 - min(|x|,1.9)) outside the unit ball and
+ *   x <- uncontract(x) * radius + center (:187-193, :215-219, :248-250); else truncation 5*voxel_size;
+ *   for each view in order: project, mask_proj, bilinear border/align_corners sample of depth
+ *   (and rgb), sdf = depth - z, fused where sdf > -trunc with the running mean of :236-241.
+ * init != 0 starts from tsdf = 1, weight = 1, rgb = 0 (the reference's initial state) ; init == 0
+ * continues from the values in tsdf / weights / rgb (views streamed in several calls).
+ * `views` is a DEVICE array of nviews descriptors.  weights may be NULL when init != 0;
+ * rgb == NULL skips the colour fusion (the reference computes and discards it when
+ * return_rgb=False).  Asynchronous on `stream`; allocates nothing. */
+int gsr_tsdf_fuse(long long n, const float* samples, int contracted, const float* center_host3,
+                  float radius, float voxel_size, int nviews, const gsr_tsdf_view* views, int init,
+                  float* tsdf, float* weights, float* rgb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,64 @@
+"""Developer helper (not a pytest): TSDF fusion throughput on a 256^3 chunk x 32 views @ 1600x1060 --
+gsr_tsdf_fuse vs the reference's per-view torch rule (restated with the same torch ops, on the GPU)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gs-sr_b200"))
+import numpy as np, torch
+from tsdf_synth import build_tsdf_case
+from gsr_b200.tsdf import TSDFFusion
+
+c = build_tsdf_case("bench")
+Ng = 256
+ax = torch.linspace(-1.2, 1.2, Ng, device="cuda")
+xx, yy, zz = torch.meshgrid(ax, ax, ax, indexing="ij")
+pts = torch.stack([xx.ravel(), yy.ravel(), zz.ravel()], -1).contiguous()
+projs = [torch.from_numpy(m).cuda() for m in c["projs"]]
+depths = [torch.from_numpy(d).cuda() for d in c["depthmaps"]]
+rgbs = [torch.from_numpy(r).cuda() for r in c["rgbmaps"]]
+center = torch.from_numpy(c["center"]).cuda(); radius = c["radius"]; vs = c["voxel_size"]
+f = TSDFFusion(projs, depths, rgbs, center=c["center"], radius=radius)
+
+
+def torch_rule(samples, return_rgb=False):
+    """mesh_utils.py:195-246 with the same torch ops (GPU tensors), the reference arm of this helper."""
+    norm = torch.linalg.norm(samples, dim=-1)
+    mask = norm > 1
+    sdf_trunc = 5 * vs * torch.ones_like(samples[:, 0])
+    sdf_trunc[mask] *= 1 / (2 - norm[mask].clamp(max=1.9))
+    mag = norm[..., None]
+    samples = torch.where(mag < 1, samples, (1 / (2 - mag) * (samples / mag))) * radius + center
+    tsdfs = torch.ones_like(samples[:, 0]); rgbo = torch.zeros((samples.shape[0], 3), device="cuda")
+    weights = torch.ones_like(samples[:, 0])
+    for i in range(len(projs)):
+        new_points = torch.cat([samples, torch.ones_like(samples[..., :1])], dim=-1) @ projs[i]
+        z = new_points[..., -1:]
+        pix = new_points[..., :2] / new_points[..., -1:]
+        mask_proj = ((pix > -1.) & (pix < 1.) & (z > 0)).all(dim=-1)
+        sd = torch.nn.functional.grid_sample(depths[i][None], pix[None, None], mode='bilinear', padding_mode='border', align_corners=True).reshape(-1, 1)
+        sr = torch.nn.functional.grid_sample(rgbs[i][None], pix[None, None], mode='bilinear', padding_mode='border', align_corners=True).reshape(3, -1).T
+        sdf = (sd - z).flatten()
+        mask_proj = mask_proj & (sdf > -sdf_trunc)
+        sdf = torch.clamp(sdf / sdf_trunc, min=-1.0, max=1.0)[mask_proj]
+        w = weights[mask_proj]; wp = w + 1
+        tsdfs[mask_proj] = (tsdfs[mask_proj] * w + sdf) / wp
+        rgbo[mask_proj] = (rgbo[mask_proj] * w[:, None] + sr[mask_proj]) / wp[:, None]
+        weights[mask_proj] = wp
+    return tsdfs
+
+
+def timed(fn, n):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, out
+
+t_ours, a = timed(lambda: f.compute_unbounded_tsdf(pts, True, vs), 5)
+t_rgb, _ = timed(lambda: f.compute_unbounded_tsdf(pts, True, vs, return_rgb=True), 3)
+t_ref, b = timed(lambda: torch_rule(pts), 2)
+n, V = pts.shape[0], len(projs)
+d = (a - b).abs()
+print(f"samples={n} views={V}: gsr_tsdf_fuse {t_ours:.2f} ms ({n*V/t_ours/1e6:.1f} G sample-views/s), with rgb {t_rgb:.2f} ms; "
+      f"torch rule {t_ref:.1f} ms -> x{t_ref/t_ours:.1f}; max|diff|={d.max().item():.3g} frac>2e-5={(d>2e-5).float().mean().item():.2e}")
+print(f"HBM algorithmic bytes {n*16/1e6:.0f} MB -> {n*16/t_ours/1e6:.1f} GB/s")

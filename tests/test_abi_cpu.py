@@ -146,3 +146,12 @@ def test_ewa_entry_points_reject_bad_arguments_without_gpu():
     assert L.gsr_dist2_knn3(0, None, None, None, None) == 0
     assert L.gsr_dist2_knn3_workspace(1000) > 1000 * 16
     assert L.gsr_gaussian_backward(0, *([0] * 3), None, 0, 0, *([None] * 4), 1.0, *([None] * 5), 1.0, 1.0, *([None] * 14), 0, None) == 0
+
+
+def test_tsdf_fuse_argument_validation_without_gpu():
+    import gsr_b200
+    L = gsr_b200.lib()
+    assert L.gsr_tsdf_fuse(-1, None, 0, None, 1.0, 0.01, 0, None, 1, None, None, None, None) == -1
+    assert L.gsr_tsdf_fuse(4, None, 0, None, 1.0, 0.01, 0, None, 1, None, None, None, None) == -1   # samples required
+    assert L.gsr_tsdf_fuse(0, None, 0, None, 1.0, 0.01, 0, None, 1, None, None, None, None) == 0    # nothing to do
+    assert b"gsr_tsdf_fuse" in L.gsr_last_error()
