@@ -54,6 +54,13 @@ def timed(fn, n):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n, out
 
+for vpl in (32, 16, 8, 4, 2):
+    f.views_per_launch = vpl
+    t, _ = timed(lambda: f.compute_unbounded_tsdf(pts, True, vs), 5)
+    t2, _ = timed(lambda: f.compute_unbounded_tsdf(pts, True, vs, return_rgb=True), 3)
+    print(f"views_per_launch={vpl}: {t:.2f} ms, with rgb {t2:.2f} ms")
+f.views_per_launch = None
+print("default groups:", f._launch_groups(1), f._launch_groups(4))
 t_ours, a = timed(lambda: f.compute_unbounded_tsdf(pts, True, vs), 5)
 t_rgb, _ = timed(lambda: f.compute_unbounded_tsdf(pts, True, vs, return_rgb=True), 3)
 t_ref, b = timed(lambda: torch_rule(pts), 2)
