@@ -1,0 +1,315 @@
+"""Caller-side mirror of ONE GS-SR 2DGS training iteration, used to exercise the drop-in rasterizer exactly
+the way GS-SR drives it and to measure train iters/s (BASELINE metric, second half).
+
+It restates, with plain torch ops, what the reference does around the rasterizer call (the reference's own
+Python cannot travel to the GPU box):
+  Trainer.train step                     gssr/engine/trainer.py:88-128 (loss.backward, loss.item, optimizer.step, zero_grad)
+  activations of the raw parameters      gssr/gaussian/vanilla_gaussian.py (exp / sigmoid / normalize, get_features cat)
+  TwoDGSScene.render                     gssr/scene/twodgs_scene.py:37-127 (means2D protocol :39-43, allmap post-processing :88-117)
+  depth_to_normal / depths_to_points     gssr/utils/point_utils.py:9-37
+  VanillaScene L1 + SSIM                 gssr/scene/vanilla_scene.py:29-69 (lambda_dssim 0.2)
+  TwoDGSScene normal / dist losses       gssr/scene/twodgs_scene.py:25-35 (lambda_normal 0.05, lambda_dist as configured)
+  densification statistics               gssr/gaussian/vanilla_gaussian.py:428-430 (viewspace grad norm, denom, max radii)
+The rasterizer is pluggable: the drop-in ``diff_surfel_rasterization`` (product) or the UNMODIFIED reference
+kernels (oracle/_ref/libref_surfel.so) behind an autograd.Function -- everything else is shared, so the iters/s
+ratio isolates the rasterizer.  Test infrastructure, not product code.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import synth
+
+
+class _RefSurfelFn(torch.autograd.Function):
+    """Reference CUDA kernels as an autograd op with the same signature/returns as the reference
+    _RasterizeGaussians (S/diff_surfel_rasterization/__init__.py:44-156)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors, opacities, scales, rotations, ref, rs):
+        color, radii, others, _ = ref.forward(rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, rs.image_width,
+                                              rs.image_height, rs.tanfovx, rs.tanfovy, means3D.contiguous(),
+                                              opacities.contiguous(), scales.contiguous(), rotations.contiguous(),
+                                              shs=None if sh is None else sh.contiguous(),
+                                              colors=None if colors is None else colors.contiguous(),
+                                              sh_degree=rs.sh_degree)
+        ctx.ref, ctx.has_sh = ref, sh is not None
+        ctx.mark_non_differentiable(radii)
+        return color, radii, others
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_others):
+        g = ctx.ref.backward(g_color, g_others)
+        return (g["means3D"], g["means2D"], g["shs"] if ctx.has_sh else None, None if ctx.has_sh else g["colors"],
+                g["opacities"], g["scales"], g["rotations"], None, None)
+
+
+class MiniTwoDGSTrainer:
+    def __init__(self, P=100_000, W=800, H=800, seed=0, impl="ours", lambda_dssim=0.2, lambda_normal=0.05,
+                 lambda_dist=100.0, depth_ratio=0.0, device="cuda"):
+        self.impl, self.W, self.H, self.device = impl, W, H, device
+        self.lambda_dssim, self.lambda_normal, self.lambda_dist, self.depth_ratio = lambda_dssim, lambda_normal, lambda_dist, depth_ratio
+        sc = synth.make_scene(P, W, H, seed=seed, sh=True)
+        self.sc = sc
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        cam = sc.cam
+        self.view, self.proj, self.campos, self.bg = t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos), t(cam.bg)
+        # raw parameters as GS-SR stores them (log-scales, logit-opacities, un-normalised quats, SH split dc / rest)
+        self.xyz = torch.nn.Parameter(t(sc.means3D))
+        self.features_dc = torch.nn.Parameter(t(sc.shs[:, :1, :]))
+        self.features_rest = torch.nn.Parameter(t(sc.shs[:, 1:, :]))
+        self.scaling = torch.nn.Parameter(torch.log(t(sc.scales)))
+        self.rotation = torch.nn.Parameter(t(sc.rotations) * 1.7)
+        op = t(sc.opacities).clamp(1e-4, 1 - 1e-4)
+        self.opacity = torch.nn.Parameter(torch.log(op / (1 - op)))
+        self.optimizer = torch.optim.Adam([
+            {"params": [self.xyz], "lr": 1.6e-4, "name": "xyz"},
+            {"params": [self.features_dc], "lr": 2.5e-3, "name": "f_dc"},
+            {"params": [self.features_rest], "lr": 2.5e-3 / 20.0, "name": "f_rest"},
+            {"params": [self.opacity], "lr": 0.05, "name": "opacity"},
+            {"params": [self.scaling], "lr": 5e-3, "name": "scaling"},
+            {"params": [self.rotation], "lr": 1e-3, "name": "rotation"}], lr=0.0, eps=1e-15)
+        self.xyz_gradient_accum = torch.zeros((P, 1), device=device)
+        self.denom = torch.zeros((P, 1), device=device)
+        self.max_radii2D = torch.zeros((P,), device=device)
+        # a fixed "ground truth" image (smooth pattern): the same for both arms
+        yy, xx = torch.meshgrid(torch.arange(H, device=device).float() / H, torch.arange(W, device=device).float() / W, indexing="ij")
+        self.gt = torch.stack([0.5 + 0.4 * torch.sin(6 * xx + 2 * yy), 0.5 + 0.4 * torch.cos(5 * yy), 0.5 + 0.4 * torch.sin(4 * (xx - yy))])
+        g1 = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)])
+        g1 = (g1 / g1.sum()).unsqueeze(1)
+        self.window = g1.mm(g1.t()).float()[None, None].expand(3, 1, 11, 11).contiguous().to(device)
+        if impl == "ours":
+            from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+            self.Settings, self.Rasterizer = GaussianRasterizationSettings, GaussianRasterizer
+        else:
+            from diff_surfel_rasterization import GaussianRasterizationSettings   # same NamedTuple as the reference's
+            from oracle.refcuda import RefSurfel
+            self.Settings, self.ref = GaussianRasterizationSettings, RefSurfel()
+
+    # ---- twodgs_scene.py:37-127 ---------------------------------------------------------------------------
+    def render(self):
+        means3D = self.xyz
+        opacity = torch.sigmoid(self.opacity)
+        scales = torch.exp(self.scaling)
+        rotations = F.normalize(self.rotation)
+        shs = torch.cat((self.features_dc, self.features_rest), dim=1)
+        screenspace_points = torch.zeros_like(means3D, dtype=means3D.dtype, requires_grad=True, device=self.device) + 0
+        screenspace_points.retain_grad()
+        rs = self.Settings(image_height=self.H, image_width=self.W, tanfovx=self.sc.cam.tanfovx, tanfovy=self.sc.cam.tanfovy,
+                           bg=self.bg, scale_modifier=1.0, viewmatrix=self.view, projmatrix=self.proj, sh_degree=3,
+                           campos=self.campos, prefiltered=False, debug=False)
+        if self.impl == "ours":
+            rendered_image, radii, allmap = self.Rasterizer(raster_settings=rs)(
+                means3D=means3D, means2D=screenspace_points, shs=shs, colors_precomp=None, opacities=opacity,
+                scales=scales, rotations=rotations, cov3D_precomp=None)
+        else:
+            rendered_image, radii, allmap = _RefSurfelFn.apply(means3D, screenspace_points, shs, None, opacity, scales,
+                                                               rotations, self.ref, rs)
+        render_alpha = allmap[1:2]
+        render_normal = allmap[2:5]
+        render_normal = (render_normal.permute(1, 2, 0) @ (self.view[:3, :3].T)).permute(2, 0, 1)
+        render_depth_median = torch.nan_to_num(allmap[5:6], 0, 0)
+        render_depth_expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
+        render_dist = allmap[6:7]
+        surf_depth = render_depth_expected * (1 - self.depth_ratio) + self.depth_ratio * render_depth_median
+        surf_normal = self.depth_to_normal(surf_depth).permute(2, 0, 1) * render_alpha.detach()
+        return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+                "radii": radii, "rend_alpha": render_alpha, "rend_dist": render_dist, "surf_normal": surf_normal,
+                "depth": surf_depth, "normal": render_normal}
+
+    # ---- point_utils.py:9-37 ------------------------------------------------------------------------------
+    def depth_to_normal(self, depth):
+        W, H = self.W, self.H
+        c2w = (self.view.T).inverse()
+        ndc2pix = torch.tensor([[W / 2, 0, 0, W / 2], [0, H / 2, 0, H / 2], [0, 0, 0, 1]]).float().to(self.device).T
+        projection_matrix = c2w.T @ self.proj
+        intrins = (projection_matrix @ ndc2pix)[:3, :3].T
+        grid_x, grid_y = torch.meshgrid(torch.arange(W, device=self.device).float(), torch.arange(H, device=self.device).float(), indexing="xy")
+        points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3)
+        rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
+        rays_o = c2w[:3, 3]
+        points = (depth.reshape(-1, 1) * rays_d + rays_o).reshape(*depth.shape[1:], 3)
+        output = torch.zeros_like(points)
+        dx = points[2:, 1:-1] - points[:-2, 1:-1]
+        dy = points[1:-1, 2:] - points[1:-1, :-2]
+        output[1:-1, 1:-1, :] = F.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
+        return output
+
+    # ---- vanilla_scene.py:29-69, twodgs_scene.py:25-35 ----------------------------------------------------
+    def ssim(self, img1, img2):
+        w, pad = self.window, 5
+        mu1, mu2 = F.conv2d(img1, w, padding=pad, groups=3), F.conv2d(img2, w, padding=pad, groups=3)
+        mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+        s1 = F.conv2d(img1 * img1, w, padding=pad, groups=3) - mu1_sq
+        s2 = F.conv2d(img2 * img2, w, padding=pad, groups=3) - mu2_sq
+        s12 = F.conv2d(img1 * img2, w, padding=pad, groups=3) - mu1_mu2
+        C1, C2 = 0.01 ** 2, 0.03 ** 2
+        return (((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean()
+
+    def loss_dict(self, out):
+        image = out["render"]
+        d = {"L1_loss": (1.0 - self.lambda_dssim) * torch.abs(image - self.gt).mean(),
+             "ssim_loss": self.lambda_dssim * (1.0 - self.ssim(image, self.gt))}
+        normal_error = (1 - (out["normal"] * out["surf_normal"]).sum(dim=0))[None]
+        d["normal_loss"] = self.lambda_normal * normal_error.mean()
+        d["dist_loss"] = self.lambda_dist * out["rend_dist"].mean()
+        return d
+
+    # ---- trainer.py:88-128 ---------------------------------------------------------------------------------
+    def step(self):
+        out = self.render()
+        losses = self.loss_dict(out)
+        loss = sum(losses.values())
+        loss.backward()
+        loss_value = loss.item()                                    # the reference's per-step host sync
+        with torch.no_grad():                                       # vanilla_gaussian.py:428-430 + max radii
+            vis = out["visibility_filter"]
+            self.max_radii2D[vis] = torch.max(self.max_radii2D[vis], out["radii"][vis].float())
+            g = out["viewspace_points"].grad
+            self.xyz_gradient_accum[vis] += torch.norm(g[vis, :2], dim=-1, keepdim=True)
+            self.denom[vis] += 1
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        return loss_value, {k: float(v.detach()) for k, v in losses.items()}
+
+
+class MiniScaffold2DGSTrainer(MiniTwoDGSTrainer):
+    """Scaffold-2DGS iteration (BASELINE config 3): anchors -> scaffold_filter.visible_filter on scales[:, :3]
+    (scaffold_scene.py:122-155) -> neural Gaussians from three MLPs with the opacity mask
+    (scaffold_scene.py:26-120) -> surfel rasterizer with colors_precomp and the stride-3 ``scaling[:, :2]`` view
+    (scaffold_2dgs_scene.py:14-19) -> 2DGS losses + scaling loss -> anchor statistics
+    (scaffold_gaussian.py:488-508: opacity_accum, anchor_demon, offset_gradient_accum, offset_denom)."""
+
+    def __init__(self, n_anchor=200_000, k=5, feat_dim=32, W=800, H=800, seed=0, impl="ours", device="cuda", **kw):
+        self.impl, self.W, self.H, self.device, self.k = impl, W, H, device, k
+        self.lambda_dssim, self.lambda_normal, self.lambda_dist, self.depth_ratio = 0.2, 0.05, kw.get("lambda_dist", 0.0), 0.0
+        self.lambda_scaling = 0.01
+        sc = synth.make_scene(n_anchor, W, H, seed=seed, scale_dims=3)
+        self.sc = sc
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        cam = sc.cam
+        self.view, self.proj, self.campos, self.bg = t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos), t(cam.bg)
+        g = torch.Generator(device="cpu").manual_seed(seed + 1)
+        self.anchor = torch.nn.Parameter(t(sc.means3D))
+        base = torch.log(t(sc.scales).mean(dim=1, keepdim=True) * 2.0)
+        self.scaling = torch.nn.Parameter(base.repeat(1, 6).contiguous())            # (N, 6) log-scales: offsets | cov
+        self.rotation = torch.nn.Parameter(t(sc.rotations), requires_grad=False)
+        self.offset = torch.nn.Parameter((torch.randn((n_anchor, k, 3), generator=g) * 0.5).to(device))
+        self.anchor_feat = torch.nn.Parameter((torch.randn((n_anchor, feat_dim), generator=g) * 0.5).to(device))
+        torch.manual_seed(seed + 2)
+        mlp = lambda o, act: torch.nn.Sequential(torch.nn.Linear(feat_dim + 3, feat_dim), torch.nn.ReLU(True),  # noqa: E731
+                                                 torch.nn.Linear(feat_dim, o), act).to(device)
+        self.mlp_opacity, self.mlp_color, self.mlp_cov = mlp(k, torch.nn.Tanh()), mlp(3 * k, torch.nn.Sigmoid()), mlp(7 * k, torch.nn.Identity())
+        params = [self.anchor, self.scaling, self.offset, self.anchor_feat] + [p for m in (self.mlp_opacity, self.mlp_color, self.mlp_cov) for p in m.parameters()]
+        self.optimizer = torch.optim.Adam(params, lr=1e-3, eps=1e-15)
+        self.opacity_accum = torch.zeros((n_anchor, 1), device=device)
+        self.anchor_demon = torch.zeros((n_anchor, 1), device=device)
+        self.offset_gradient_accum = torch.zeros((n_anchor * k, 1), device=device)
+        self.offset_denom = torch.zeros((n_anchor * k, 1), device=device)
+        yy, xx = torch.meshgrid(torch.arange(H, device=device).float() / H, torch.arange(W, device=device).float() / W, indexing="ij")
+        self.gt = torch.stack([0.5 + 0.4 * torch.sin(6 * xx + 2 * yy), 0.5 + 0.4 * torch.cos(5 * yy), 0.5 + 0.4 * torch.sin(4 * (xx - yy))])
+        g1 = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)])
+        g1 = (g1 / g1.sum()).unsqueeze(1)
+        self.window = g1.mm(g1.t()).float()[None, None].expand(3, 1, 11, 11).contiguous().to(device)
+        from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+        import scaffold_filter
+        self.Settings, self.Rasterizer, self.filter_mod = GaussianRasterizationSettings, GaussianRasterizer, scaffold_filter
+        if impl != "ours":
+            from oracle.refcuda import RefSurfel
+            self.ref = RefSurfel()
+
+    def prefilter_voxel(self):
+        scales = torch.exp(self.scaling)
+        if self.impl == "ours":
+            fs = self.filter_mod.GaussianRasterizationSettings(self.H, self.W, self.sc.cam.tanfovx, self.sc.cam.tanfovy, self.bg, 1.0,
+                                                               self.view, self.proj, 0, self.campos, False, False)
+            radii = self.filter_mod.GaussianRasterizer(fs).visible_filter(means3D=self.anchor, scales=scales[:, :3],
+                                                                          rotations=self.rotation, cov3D_precomp=None)
+        else:
+            from oracle.refcuda import ref_visible_filter
+            radii = ref_visible_filter(self.anchor.detach(), scales[:, :3].detach().contiguous(), self.rotation, self.view, self.proj,
+                                       self.W, self.H, self.sc.cam.tanfovx, self.sc.cam.tanfovy)
+        return radii > 0
+
+    def generate_neural_gaussians(self, visible_mask):
+        k = self.k
+        feat, anchor = self.anchor_feat[visible_mask], self.anchor[visible_mask]
+        grid_offsets, grid_scaling = self.offset[visible_mask], torch.exp(self.scaling)[visible_mask]
+        ob_view = anchor - self.campos
+        ob_view = ob_view / ob_view.norm(dim=1, keepdim=True)
+        x = torch.cat([feat, ob_view], dim=1)
+        neural_opacity = self.mlp_opacity(x).reshape([-1, 1])
+        mask = (neural_opacity > 0.0).view(-1)
+        opacity = neural_opacity[mask]
+        color = self.mlp_color(x).reshape([anchor.shape[0] * k, 3])
+        scale_rot = self.mlp_cov(x).reshape([anchor.shape[0] * k, 7])
+        offsets = grid_offsets.view([-1, 3])
+        rep = torch.cat([grid_scaling, anchor], dim=-1).repeat_interleave(k, dim=0)
+        masked = torch.cat([rep, color, scale_rot, offsets], dim=-1)[mask]
+        scaling_repeat, repeat_anchor, color, scale_rot, offsets = masked.split([6, 3, 3, 7, 3], dim=-1)
+        scaling = scaling_repeat[:, 3:] * torch.sigmoid(scale_rot[:, :3])
+        rot = F.normalize(scale_rot[:, 3:7])
+        xyz = repeat_anchor + offsets * scaling_repeat[:, :3]
+        return xyz, color, opacity, scaling, rot, neural_opacity, mask
+
+    def step(self):
+        visible = self.prefilter_voxel()
+        xyz, color, opacity, scaling3, rot, neural_opacity, mask = self.generate_neural_gaussians(visible)
+        scaling = scaling3[:, :2]                                   # stride-3 view, as GS-SR passes it
+        screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
+        screenspace_points.retain_grad()
+        rs = self.Settings(image_height=self.H, image_width=self.W, tanfovx=self.sc.cam.tanfovx, tanfovy=self.sc.cam.tanfovy,
+                           bg=self.bg, scale_modifier=1.0, viewmatrix=self.view, projmatrix=self.proj, sh_degree=0,
+                           campos=self.campos, prefiltered=False, debug=False)
+        if self.impl == "ours":
+            image, radii, allmap = self.Rasterizer(raster_settings=rs)(
+                means3D=xyz, means2D=screenspace_points, shs=None, colors_precomp=color, opacities=opacity,
+                scales=scaling, rotations=rot, cov3D_precomp=None)
+        else:
+            image, radii, allmap = _RefSurfelFn.apply(xyz, screenspace_points, None, color, opacity, scaling, rot, self.ref, rs)
+        render_alpha = allmap[1:2]
+        render_normal = (allmap[2:5].permute(1, 2, 0) @ (self.view[:3, :3].T)).permute(2, 0, 1)
+        depth = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
+        surf_normal = self.depth_to_normal(depth).permute(2, 0, 1) * render_alpha.detach()
+        out = {"render": image, "normal": render_normal, "surf_normal": surf_normal, "rend_dist": allmap[6:7]}
+        losses = self.loss_dict(out)
+        losses["scaling_loss"] = self.lambda_scaling * scaling.prod(dim=1).mean()
+        loss = sum(losses.values())
+        loss.backward()
+        loss_value = loss.item()
+        with torch.no_grad():                                       # scaffold_gaussian.py:488-508
+            update_filter = radii > 0
+            temp_opacity = neural_opacity.clone().view(-1).detach()
+            temp_opacity[temp_opacity < 0] = 0
+            self.opacity_accum[visible] += temp_opacity.view([-1, self.k]).sum(dim=1, keepdim=True)
+            self.anchor_demon[visible] += 1
+            av = visible.unsqueeze(dim=1).repeat([1, self.k]).view(-1)
+            combined = torch.zeros_like(self.offset_gradient_accum, dtype=torch.bool).squeeze(dim=1)
+            combined[av] = mask
+            tmp = combined.clone()
+            combined[tmp] = update_filter
+            grad_norm = torch.norm(screenspace_points.grad[update_filter, :2], dim=-1, keepdim=True)
+            self.offset_gradient_accum[combined] += grad_norm
+            self.offset_denom[combined] += 1
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        self.last = dict(visible=int(visible.sum()), gaussians=int(mask.sum()), rendered=int(update_filter.sum()))
+        return loss_value, {k_: float(v.detach()) for k_, v in losses.items()}
+
+
+def measure_iters_per_s(impl, P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, scaffold=False):
+    tr = MiniScaffold2DGSTrainer(P, W=W, H=H, seed=seed, impl=impl) if scaffold else MiniTwoDGSTrainer(P, W, H, seed=seed, impl=impl)
+    for _ in range(warmup):
+        tr.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        last = tr.step()
+    e1.record()
+    torch.cuda.synchronize()
+    return iters / (e0.elapsed_time(e1) * 1e-3), last
