@@ -19,3 +19,9 @@ for N in (400_000,):
         b, _ = measure_iters_per_s("reference", N, 1600, 1060, iters=12, scaffold=True)
         msg += f", reference kernels {b:.1f} it/s, x{a/b:.2f}"
     print(msg)
+a, _ = measure_iters_per_s("ours", 1_000_000, 1600, 900, iters=12, pgsr=True)
+msg = f"PGSR flow (2 views/iter), P=1M, 1600x900: ours {a:.1f} it/s"
+if refcuda.available("plane"):
+    b, _ = measure_iters_per_s("reference", 1_000_000, 1600, 900, iters=12, pgsr=True)
+    msg += f", reference kernels {b:.1f} it/s, x{a/b:.2f}"
+print(msg)

@@ -61,3 +61,25 @@ def test_scaffold_2dgs_iteration_matches_reference_kernels():
     assert float((ga - gb).norm() / gb.norm()) <= 1e-3
     assert torch.equal(a.offset_denom, b.offset_denom) and torch.equal(a.anchor_demon, b.anchor_demon)
     assert torch.allclose(a.opacity_accum, b.opacity_accum)
+
+
+def test_pgsr_iteration_matches_reference_kernels():
+    """config-4 flow: two views per iteration through the plane rasterizer, autograd-built all_map, means2D_abs, out_observe."""
+    from oracle import refcuda
+    if not refcuda.available("plane"):
+        pytest.skip("oracle/_ref/libref_plane.so did not travel")
+    from train_harness import MiniPGSRTrainer
+    kw = dict(P=20000, W=256, H=144, seed=13)
+    a, b = MiniPGSRTrainer(impl="ours", **kw), MiniPGSRTrainer(impl="reference", **kw)
+    la, da = a.step()
+    lb, db = b.step()
+    assert a.last == b.last and a.last["observed"] > 1000, (a.last, b.last)
+    for k in da:
+        assert abs(da[k] - db[k]) <= 1e-5 * max(abs(db[k]), 1e-3), (k, da[k], db[k])
+    for x, y in ((a.xyz_gradient_accum, b.xyz_gradient_accum), (a.xyz_gradient_accum_abs, b.xyz_gradient_accum_abs)):
+        assert float((x.double() - y.double()).norm() / y.double().norm()) <= 1e-3
+    assert torch.equal(a.denom, b.denom) and torch.equal(a.max_radii2D, b.max_radii2D)
+    for _ in range(2):
+        la, _ = a.step()
+        lb, _ = b.step()
+    assert abs(la - lb) <= 2e-3 * abs(lb), (la, lb)

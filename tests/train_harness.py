@@ -301,8 +301,145 @@ class MiniScaffold2DGSTrainer(MiniTwoDGSTrainer):
         return loss_value, {k_: float(v.detach()) for k_, v in losses.items()}
 
 
-def measure_iters_per_s(impl, P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, scaffold=False):
-    tr = MiniScaffold2DGSTrainer(P, W=W, H=H, seed=seed, impl=impl) if scaffold else MiniTwoDGSTrainer(P, W, H, seed=seed, impl=impl)
+class _RefPlaneFn(torch.autograd.Function):
+    """Reference diff-plane-rasterization kernels as an autograd op (L/diff_plane_rasterization/__init__.py:48-171)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, means2D_abs, colors, opacities, scales, rotations, all_map, ref, rs):
+        o = ref.forward(rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, rs.image_width, rs.image_height, rs.tanfovx, rs.tanfovy,
+                        means3D.contiguous(), opacities.contiguous(), scales.contiguous(), rotations.contiguous(),
+                        colors=colors.contiguous(), all_map=all_map.contiguous(), render_geo=True)
+        ctx.ref = ref
+        ctx.mark_non_differentiable(o["radii"], o["observe"])
+        return o["color"], o["radii"], o["observe"], o["out_all_map"], o["plane_depth"]
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_obs, g_all_map, g_plane_depth):
+        g = ctx.ref.backward(g_color, g_all_map, g_plane_depth)
+        return (g["means3D"], g["means2D"], g["means2D_abs"], g["colors"], g["opacities"], g["scales"], g["rotations"],
+                g["all_map"], None, None)
+
+
+class MiniPGSRTrainer(MiniTwoDGSTrainer):
+    """PGSR iteration (BASELINE config 4): the reference view AND one neighbour view are rendered through the
+    plane rasterizer (pgsr_scene.py:206-224), per-Gaussian all_map = [n_view, 1, |n_view . p_view|] built with autograd
+    from the smallest-scale axis (pgsr_scene.py:238-256, 295-302), means2D / means2D_abs protocol (:262-268), depth normal
+    from plane_depth (graphics_utils.py:110-146), L1 + SSIM + single-view normal loss (pgsr_scene.py:100-113, without the
+    image-gradient weight) + a cross-view plane-depth term standing in for the multi-view geometric loss, densification
+    statistics incl. the abs accumulator and out_observe gating (pgsr_gaussian.py:157-171)."""
+
+    def __init__(self, P=100_000, W=800, H=450, seed=0, impl="ours", device="cuda"):
+        self.impl, self.W, self.H, self.device = impl, W, H, device
+        self.lambda_dssim, self.lambda_normal = 0.2, 0.015
+        sc = synth.make_scene(P, W, H, seed=seed, scale_dims=3)
+        self.sc = sc
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        q = np.array([1.0, 0.004, -0.006, 0.002]); q /= np.linalg.norm(q)
+        cams = [sc.cam, synth.make_camera(W, H, R=synth.quat_to_rot(q), t=np.array([0.06, -0.02, 0.03]))]
+        self.cams = [dict(view=t(c.viewmatrix), proj=t(c.projmatrix), campos=t(c.campos), tanfovx=c.tanfovx, tanfovy=c.tanfovy) for c in cams]
+        self.bg = t(sc.cam.bg)
+        self.xyz = torch.nn.Parameter(t(sc.means3D))
+        self.colors_raw = torch.nn.Parameter(torch.logit(t(sc.colors).clamp(1e-3, 1 - 1e-3)))
+        self.scaling = torch.nn.Parameter(torch.log(t(sc.scales)))
+        self.rotation = torch.nn.Parameter(t(sc.rotations))
+        op = t(sc.opacities).clamp(1e-4, 1 - 1e-4)
+        self.opacity = torch.nn.Parameter(torch.log(op / (1 - op)))
+        self.optimizer = torch.optim.Adam([self.xyz, self.colors_raw, self.scaling, self.rotation, self.opacity], lr=1e-3, eps=1e-15)
+        z = lambda *sh: torch.zeros(sh, device=device)  # noqa: E731
+        self.xyz_gradient_accum, self.xyz_gradient_accum_abs, self.denom, self.max_radii2D = z(P, 1), z(P, 1), z(P, 1), z(P)
+        yy, xx = torch.meshgrid(torch.arange(H, device=device).float() / H, torch.arange(W, device=device).float() / W, indexing="ij")
+        self.gt = torch.stack([0.5 + 0.4 * torch.sin(6 * xx + 2 * yy), 0.5 + 0.4 * torch.cos(5 * yy), 0.5 + 0.4 * torch.sin(4 * (xx - yy))])
+        g1 = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)])
+        g1 = (g1 / g1.sum()).unsqueeze(1)
+        self.window = g1.mm(g1.t()).float()[None, None].expand(3, 1, 11, 11).contiguous().to(device)
+        from diff_plane_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+        self.Settings, self.Rasterizer = GaussianRasterizationSettings, GaussianRasterizer
+        if impl != "ours":
+            from oracle.refcuda import RefGauss
+            self.refs = [RefGauss(plane=True), RefGauss(plane=True)]     # one context per view kept alive until backward
+
+    @staticmethod
+    def quaternion_to_matrix(q):                                        # pytorch3d.transforms.quaternion_to_matrix
+        r, i, j, k = torch.unbind(q, -1)
+        two_s = 2.0 / (q * q).sum(-1)
+        o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                         two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                         two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+        return o.reshape(q.shape[:-1] + (3, 3))
+
+    def normal_from_depth(self, depth, cam):                            # graphics_utils.py:80-146 (offset=None)
+        H, W = depth.shape
+        fx, fy = W / (2 * cam["tanfovx"]), H / (2 * cam["tanfovy"])
+        ix, iy = torch.meshgrid(torch.arange(W, device=self.device).float(), torch.arange(H, device=self.device).float(), indexing="xy")
+        xyz = torch.stack([(ix - W / 2) / fx * depth, (iy - H / 2) / fy * depth, depth], -1)
+        l2r = xyz[1:H - 1, 2:W] - xyz[1:H - 1, 0:W - 2]
+        b2t = xyz[0:H - 2, 1:W - 1] - xyz[2:H, 1:W - 1]
+        n = F.normalize(torch.cross(l2r, b2t, dim=-1), p=2, dim=-1)
+        return F.pad(n.permute(2, 0, 1), (1, 1, 1, 1), mode="constant")
+
+    def render_view(self, vi):
+        cam = self.cams[vi]
+        means3D, opacity = self.xyz, torch.sigmoid(self.opacity)
+        scales, rotations, colors = torch.exp(self.scaling), F.normalize(self.rotation), torch.sigmoid(self.colors_raw)
+        sp = torch.zeros_like(means3D, requires_grad=True) + 0
+        sp_abs = torch.zeros_like(means3D, requires_grad=True) + 0
+        sp.retain_grad(); sp_abs.retain_grad()
+        rs = self.Settings(image_height=self.H, image_width=self.W, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=self.bg,
+                           scale_modifier=1.0, viewmatrix=cam["view"], projmatrix=cam["proj"], sh_degree=0, campos=cam["campos"],
+                           prefiltered=False, render_geo=True, debug=False)
+        Rm = self.quaternion_to_matrix(rotations)
+        idx = scales.min(dim=-1)[1][..., None, None].expand(-1, 3, -1)
+        normal_global = Rm.gather(2, idx).squeeze(dim=2)
+        neg = (normal_global * (cam["campos"] - means3D)).sum(-1) < 0.0
+        normal_global = torch.where(neg[:, None], -normal_global, normal_global)
+        local_normal = normal_global @ cam["view"][:3, :3]
+        pts_in_cam = means3D @ cam["view"][:3, :3] + cam["view"][3, :3]
+        local_distance = (local_normal * pts_in_cam).sum(-1).abs()
+        all_map = torch.cat([local_normal, torch.ones_like(local_distance)[:, None], local_distance[:, None]], dim=1)
+        if self.impl == "ours":
+            image, radii, observe, out_all_map, plane_depth = self.Rasterizer(raster_settings=rs)(
+                means3D=means3D, means2D=sp, means2D_abs=sp_abs, shs=None, colors_precomp=colors, opacities=opacity,
+                scales=scales, rotations=rotations, all_map=all_map, cov3D_precomp=None)
+        else:
+            image, radii, observe, out_all_map, plane_depth = _RefPlaneFn.apply(means3D, sp, sp_abs, colors, opacity, scales,
+                                                                                rotations, all_map, self.refs[vi], rs)
+        rendered_normal, rendered_alpha = out_all_map[0:3], out_all_map[3:4]
+        depth_normal = self.normal_from_depth(plane_depth.squeeze(), cam) * rendered_alpha.detach()
+        return dict(render=image, viewspace_points=sp, viewspace_points_abs=sp_abs, visibility_filter=radii > 0, radii=radii,
+                    out_observe=observe, rendered_normal=rendered_normal, plane_depth=plane_depth,
+                    rendered_distance=out_all_map[4:5], depth_normal=depth_normal)
+
+    def step(self):
+        ref, near = self.render_view(0), self.render_view(1)
+        image = ref["render"]
+        losses = {"L1_loss": (1.0 - self.lambda_dssim) * torch.abs(image - self.gt).mean(),
+                  "ssim_loss": self.lambda_dssim * (1.0 - self.ssim(image, self.gt)),
+                  "normal_loss": self.lambda_normal * ((ref["depth_normal"] - ref["rendered_normal"]).abs().sum(0)).mean(),
+                  "geo_loss": 0.03 * (ref["plane_depth"] - near["plane_depth"]).abs().clamp(max=1.0).mean()
+                              + 0.01 * (ref["rendered_distance"] - near["rendered_distance"]).abs().clamp(max=1.0).mean()}
+        loss = sum(losses.values())
+        loss.backward()
+        loss_value = loss.item()
+        with torch.no_grad():                                           # pgsr_gaussian.py:157-171
+            vis, radii = ref["visibility_filter"], ref["radii"]
+            m = (ref["out_observe"] > 0) & vis
+            self.max_radii2D[m] = torch.max(self.max_radii2D[m], radii[m].float())
+            self.xyz_gradient_accum[vis] += torch.norm(ref["viewspace_points"].grad[vis, :2], dim=-1, keepdim=True)
+            self.xyz_gradient_accum_abs[vis] += torch.norm(ref["viewspace_points_abs"].grad[vis, :2], dim=-1, keepdim=True)
+            self.denom[vis] += 1
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        self.last = dict(observed=int((ref["out_observe"] > 0).sum()), visible=int(vis.sum()))
+        return loss_value, {k_: float(v.detach()) for k_, v in losses.items()}
+
+
+def measure_iters_per_s(impl, P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, scaffold=False, pgsr=False):
+    if pgsr:
+        tr = MiniPGSRTrainer(P, W=W, H=H, seed=seed, impl=impl)
+    elif scaffold:
+        tr = MiniScaffold2DGSTrainer(P, W=W, H=H, seed=seed, impl=impl)
+    else:
+        tr = MiniTwoDGSTrainer(P, W, H, seed=seed, impl=impl)
     for _ in range(warmup):
         tr.step()
     torch.cuda.synchronize()
