@@ -93,14 +93,27 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-    capture of the same workload (profiles/traffic.json), or None."""
+def ncu_traffic(kernel, key="dram_bytes"):
+    """dram__bytes_read.sum + dram__bytes_write.sum (or another figure) per launch from the committed
+    ncu --set full capture of the same workload (profiles/traffic.json), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)[kernel]["dram_bytes"]
+            return json.load(f)[kernel][key]
     except Exception:
         return None
+
+
+def issue_side_bound(kernel, kernel_ms, sm_mhz, default_workload):
+    """The render kernels are instruction-issue bound, not HBM bound: warp
+    instructions per launch (ncu smsp__inst_executed.sum of the committed capture of the default
+    workload) / live kernel time, against 148 SMs x 4 schedulers x 1 warp-instruction per clock."""
+    inst = ncu_traffic(kernel, "inst")
+    if inst is None or not default_workload or not sm_mhz:
+        return None
+    peak = 148 * 4 * sm_mhz * 1e6
+    ach = inst / (kernel_ms * 1e-3)
+    return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
+            "inst_per_launch": inst, "source": "profiles/traffic.json (ncu smsp__inst_executed.sum) / live cudaEvent time"}
 
 
 def algorithmic_bytes(P, V, R, N):
@@ -394,7 +407,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": f"gsr::surfel_{dom}", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                          "algorithmic_bytes": ab[dom], "kernel_ms": r["kernel_ms"][dom],
-                         "whole_step_frac": ab["whole_step"] / (r["ms_resident"] / args.steps * 1e-3) / 1e9 / peak},
+                         "whole_step_frac": ab["whole_step"] / (r["ms_resident"] / args.steps * 1e-3) / 1e9 / peak,
+                         "side_bound": issue_side_bound(dom, r["kernel_ms"][dom], (r["clocks"] or {}).get("sm_mhz"),
+                                                        (args.P, args.W, args.H) == (P_DEFAULT, W_DEFAULT, H_DEFAULT))},
             "kernel_ms": r["kernel_ms"],
             "stats": {"num_rendered": R, "visible": r["V"], "pixels": N, "checksum": r["checksum"]},
         })
