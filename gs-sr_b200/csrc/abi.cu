@@ -19,6 +19,9 @@ __global__ void surfel_preprocess_bwd(int, int, int, const float*, const float2*
                                       const GeomRec*, const uint8_t*, const float*, float*, float*, float*,
                                       float*, float*, float*, float*, float*, float*);
 __global__ void mark_visible_kernel(int, const float*, const ViewParams, uint8_t*);
+cudaError_t launch_sh_forward(int, int, int, const float*, const float*, const float*, const int*, float*, uint8_t*, cudaStream_t);
+cudaError_t launch_sh_backward(int, int, int, const float*, const float*, const float*, const uint8_t*, const int*, const float*,
+                               float*, float*, cudaStream_t);
 __global__ void tile_scan(int, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, const int*);
 __global__ void scatter_keys(int, const float*, const float*, int, const CullRec*, const float*, const int*,
                              const uint32_t*, int, int, uint32_t*, uint64_t*);
@@ -213,6 +216,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     if (P > 0 && ((shs == nullptr) == (colors_precomp == nullptr))) { set_error("provide exactly one of shs / colors_precomp"); return GSR_E_INVALID; }
     if (P > 0 && (((scales == nullptr) || (rotations == nullptr)) == (transMat_precomp == nullptr))) { set_error("provide exactly one of scales+rotations / transMat_precomp"); return GSR_E_INVALID; }
     if (P > 0 && shs && !cam_pos) { set_error("cam_pos required with shs"); return GSR_E_INVALID; }
+    if (P > 0 && shs && (M < 1 || M > 16)) { set_error("shs: M = %d coefficients per channel, supported 1..16 (degree <= 3)", M); return GSR_E_INVALID; }
     const int W = width, H = height;
     const size_t N = (size_t)W * H;
 
@@ -244,9 +248,11 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
 
         prof_begin(GSR_PROF_PREPROCESS_FWD, s);
         surfel_preprocess_fwd<<<(P + 255) / 256, 256, 0, s>>>(
-            P, D, M, means3D, (const float2*)scales, (const float4*)rotations, opacities, shs, transMat_precomp,
-            colors_precomp != nullptr, vc, prefiltered != 0, no_cull(), radii, gw.geom, gw.cull, gw.depths, gw.masks,
+            P, D, M, means3D, (const float2*)scales, (const float4*)rotations, opacities, nullptr, transMat_precomp,
+            true, vc, prefiltered != 0, no_cull(), radii, gw.geom, gw.cull, gw.depths, gw.masks,
             iw.tile_count, gw.rgb, gw.clamped, gw.flags);
+        // SH -> RGB runs as its own warp-cooperative, coalesced kernel (sh.cu) on the visible Gaussians
+        if (shs) GSR_CUDA_CHECK(launch_sh_forward(P, D, M, means3D, cam_pos, shs, radii, gw.rgb, gw.clamped, s));
         prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         prof_begin(GSR_PROF_SCAN, s);
@@ -356,9 +362,11 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
     const bool precomp = (scales == nullptr);
     prof_begin(GSR_PROF_PREPROCESS_BWD, s);
     surfel_preprocess_bwd<<<(P + 255) / 256, 256, 0, s>>>(
-        P, D, M, means3D, (const float2*)scales, (const float4*)rotations, shs, precomp, vc, Wb, Hb, radii,
+        P, D, M, means3D, (const float2*)scales, (const float4*)rotations, nullptr, precomp, vc, Wb, Hb, radii,
         gw.geom, gw.clamped, bw.gacc, dL_dmean2D, dL_dnormal, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dtransMat,
-        shs ? dL_dsh : nullptr, dL_dscale, dL_drot);
+        nullptr, dL_dscale, dL_drot);
+    // dL/dsh (fully written) and the view-direction term of dL/dmean3D: coalesced SH kernel (sh.cu)
+    if (shs && M > 0) GSR_CUDA_CHECK(launch_sh_backward(P, D, M, means3D, campos, shs, gw.clamped, radii, dL_dcolor, dL_dsh, dL_dmean3D, s));
     prof_end(GSR_PROF_PREPROCESS_BWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
     if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -413,6 +421,7 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
     if (P > 0 && ((a.shs == nullptr) == (a.colors_precomp == nullptr))) { set_error("provide exactly one of shs / colors_precomp"); return GSR_E_INVALID; }
     if (P > 0 && (((a.scales == nullptr) || (a.rotations == nullptr)) == (a.cov3D_precomp == nullptr))) { set_error("provide exactly one of scales+rotations / cov3D_precomp"); return GSR_E_INVALID; }
     if (P > 0 && a.shs && !a.cam_pos) { set_error("cam_pos required with shs"); return GSR_E_INVALID; }
+    if (P > 0 && a.shs && (a.M < 1 || a.M > 16)) { set_error("shs: M = %d coefficients per channel, supported 1..16 (degree <= 3)", a.M); return GSR_E_INVALID; }
     if (a.plane && (!a.out_observe || (a.geo && (!a.out_all_map || !a.out_plane_depth || (P > 0 && !a.all_map))))) {
         set_error("%s: out_observe / out_all_map / out_plane_depth / all_map required", who); return GSR_E_INVALID;
     }
@@ -447,9 +456,10 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
         GSR_CUDA_CHECK(cudaMemsetAsync(gw.flags, 0, 32 * sizeof(int), s));
         prof_begin(GSR_PROF_PREPROCESS_FWD, s);
         ewa_preprocess_fwd<false><<<(P + 255) / 256, 256, 0, s>>>(
-            P, a.D, a.M, a.means3D, a.scales, (const float4*)a.rotations, a.opacities, a.shs, a.cov3D_precomp,
-            a.colors_precomp != nullptr, vc, focal_x, focal_y, a.tan_fovx, a.tan_fovy, a.prefiltered != 0, no_cull(),
+            P, a.D, a.M, a.means3D, a.scales, (const float4*)a.rotations, a.opacities, nullptr, a.cov3D_precomp,
+            true, vc, focal_x, focal_y, a.tan_fovx, a.tan_fovy, a.prefiltered != 0, no_cull(),
             a.radii, gw.geom, gw.cull, gw.depths, gw.masks, iw.tile_count, gw.rgb, gw.clamped, gw.flags);
+        if (a.shs) GSR_CUDA_CHECK(launch_sh_forward(P, a.D, a.M, a.means3D, a.cam_pos, a.shs, a.radii, gw.rgb, gw.clamped, s));
         prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         prof_begin(GSR_PROF_SCAN, s);
@@ -567,10 +577,11 @@ static int ewa_backward(const EwaBwdArgs& a, const char* who) {
     }
     prof_begin(GSR_PROF_PREPROCESS_BWD, s);
     ewa_preprocess_bwd<<<(P + 255) / 256, 256, 0, s>>>(
-        P, a.D, a.M, a.means3D, a.scales, (const float4*)a.rotations, a.shs, a.cov3D_precomp, vc, focal_x, focal_y,
+        P, a.D, a.M, a.means3D, a.scales, (const float4*)a.rotations, nullptr, a.cov3D_precomp, vc, focal_x, focal_y,
         a.tan_fovx, a.tan_fovy, a.radii, gw.clamped, bw.gacc, a.dL_dmean2D, a.plane ? a.dL_dmean2D_abs : nullptr,
-        a.dL_dconic, a.dL_dopacity, a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D, a.shs ? a.dL_dsh : nullptr,
+        a.dL_dconic, a.dL_dopacity, a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D, nullptr,
         a.scales ? a.dL_dscale : nullptr, a.scales ? a.dL_drot : nullptr, a.plane ? a.dL_dall_map : nullptr);
+    if (a.shs && a.M > 0) GSR_CUDA_CHECK(launch_sh_backward(P, a.D, a.M, a.means3D, a.campos, a.shs, gw.clamped, a.radii, a.dL_dcolor, a.dL_dsh, a.dL_dmean3D, s));
     prof_end(GSR_PROF_PREPROCESS_BWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
     if (a.debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -143,11 +143,8 @@ ewa_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D, const
         radius_out = ri;
         if (kRadiiOnly) break;
 
-        if (!has_colors) {
-            const float3 c = sh_to_rgb(D, M, p, make_float3(__ldg(vc.campos), __ldg(vc.campos + 1), __ldg(vc.campos + 2)),
-                                       shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx);
-            rgb[3 * (size_t)idx + 0] = c.x; rgb[3 * (size_t)idx + 1] = c.y; rgb[3 * (size_t)idx + 2] = c.z;
-        }
+        // SH -> RGB is evaluated by sh_forward_kernel (sh.cu) on the Gaussians this kernel keeps (radii > 0)
+        (void)has_colors; (void)shs; (void)rgb; (void)clamped; (void)D; (void)M;
         const float opa = __ldg(opacities + idx);
         // contribution ellipse {conic.x dx^2 + 2 conic.y dx dy + conic.z dy^2 <= tau}, tau = 2 ln(255 o):
         // alpha >= 1/255 only inside it (G/forward.cu:336-347)
@@ -219,10 +216,7 @@ ewa_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D, const
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float3 dscale = make_float3(0.f, 0.f, 0.f);
     float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (dL_dsh != nullptr) {
-        float* o = dL_dsh + (size_t)idx * M * 3;
-        for (int j = 0; j < 3 * M; j++) o[j] = 0.f;
-    }
+    (void)dL_dsh; (void)shs; (void)clamped; (void)D; (void)M;   // SH backward lives in sh.cu
     if (radii[idx] > 0) {
         float view[16];
         load16(vc.view, view);
@@ -287,12 +281,7 @@ ewa_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D, const
         dmean.x += (pm[0] * m_w - pm[3] * mul1) * dm2x + (pm[1] * m_w - pm[3] * mul2) * dm2y;
         dmean.y += (pm[4] * m_w - pm[7] * mul1) * dm2x + (pm[5] * m_w - pm[7] * mul2) * dm2y;
         dmean.z += (pm[8] * m_w - pm[11] * mul1) * dm2x + (pm[9] * m_w - pm[11] * mul2) * dm2y;
-        if (shs != nullptr) {
-            const float3 dm = sh_to_rgb_bwd(D, M, p, make_float3(__ldg(vc.campos), __ldg(vc.campos + 1), __ldg(vc.campos + 2)),
-                                            shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx, dcol,
-                                            dL_dsh + (size_t)idx * M * 3);
-            dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
-        }
+        // SH backward: sh_backward_kernel (sh.cu) runs after this kernel and accumulates into dL_dmean3D
         // ---- cov3D -> scale, quaternion (G/backward.cu:278-343): M = S R^T, dL/dM = 2 M dSigma
         if (cov3D_precomp == nullptr) {
             float Rs[3][3];

@@ -69,22 +69,22 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, int M, float3 mean, float3 
     sh_basis(deg, dir.x * inv, dir.y * inv, dir.z * inv, b);
     int n = min(sh_count(deg), M);
     float3 c = make_float3(0.f, 0.f, 0.f);
-    for (int k = 0; k < n; k++) {
-        c.x += b[k] * __ldg(sh + 3 * k + 0);
-        c.y += b[k] * __ldg(sh + 3 * k + 1);
-        c.z += b[k] * __ldg(sh + 3 * k + 2);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k >= n) break;
+        c.x += b[k] * sh[3 * k + 0];      // plain loads: `sh` may point to global OR shared memory (sh.cu)
+        c.y += b[k] * sh[3 * k + 1];
+        c.z += b[k] * sh[3 * k + 2];
     }
     c.x += 0.5f; c.y += 0.5f; c.z += 0.5f;
     clamped[0] = c.x < 0.f; clamped[1] = c.y < 0.f; clamped[2] = c.z < 0.f;
     return make_float3(fmaxf(c.x, 0.f), fmaxf(c.y, 0.f), fmaxf(c.z, 0.f));
 }
 
-// Writes dL/dsh for the first (deg+1)^2 coefficients (caller zero-fills the rest)
-// and returns the mean gradient that flows through the view direction.
-__device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, int M, float3 mean, float3 campos,
-                                                const float* __restrict__ sh,
-                                                const uint8_t* __restrict__ clamped, float3 dL_dcolor,
-                                                float* __restrict__ dL_dsh) {
+// Backward, in place (sh.cu): `c` holds the 3*M coefficients of one Gaussian on entry and
+// dL/dsh (zeros above the active degree) on exit; returns the mean gradient through the view direction.
+__device__ __forceinline__ float3 sh_to_rgb_bwd_inplace(int deg, int M, float3 mean, float3 campos, float* c,
+                                                        const uint8_t* __restrict__ clamped, float3 dL_dcolor) {
     float3 d0 = make_float3(mean.x - campos.x, mean.y - campos.y, mean.z - campos.z);
     float sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
     float inv = 1.0f / sqrtf(sum2);
@@ -97,14 +97,16 @@ __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, int M, float3 mean, flo
     sh_basis_grad(deg, x, y, z, g);
     int n = min(sh_count(deg), M);
     float3 ddir = make_float3(0.f, 0.f, 0.f);
-    for (int k = 0; k < n; k++) {
-        dL_dsh[3 * k + 0] = b[k] * dc.x;
-        dL_dsh[3 * k + 1] = b[k] * dc.y;
-        dL_dsh[3 * k + 2] = b[k] * dc.z;
-        float s = __ldg(sh + 3 * k + 0) * dc.x + __ldg(sh + 3 * k + 1) * dc.y + __ldg(sh + 3 * k + 2) * dc.z;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k >= n) break;
+        float s = c[3 * k + 0] * dc.x + c[3 * k + 1] * dc.y + c[3 * k + 2] * dc.z;
+        c[3 * k + 0] = b[k] * dc.x;
+        c[3 * k + 1] = b[k] * dc.y;
+        c[3 * k + 2] = b[k] * dc.z;
         ddir.x += g[k].x * s; ddir.y += g[k].y * s; ddir.z += g[k].z * s;
     }
-    // Jacobian of v -> v/|v| (dnormvdv, S/auxiliary.h:130-140)
+    for (int j = 3 * n; j < 3 * M; j++) c[j] = 0.f;
     float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
     return make_float3(
         ((sum2 - d0.x * d0.x) * ddir.x - d0.y * d0.x * ddir.y - d0.z * d0.x * ddir.z) * inv32,

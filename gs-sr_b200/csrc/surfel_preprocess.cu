@@ -128,11 +128,8 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
         get_rect(cx, cy, ri, vc.gx, vc.gy, x0, y0, x1, y1);
         if ((x1 - x0) * (y1 - y0) == 0) break;
 
-        if (!has_colors) {
-            float3 c = sh_to_rgb(D, M, p, make_float3(__ldg(vc.campos), __ldg(vc.campos + 1), __ldg(vc.campos + 2)),
-                                 shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx);
-            rgb[3 * (size_t)idx + 0] = c.x; rgb[3 * (size_t)idx + 1] = c.y; rgb[3 * (size_t)idx + 2] = c.z;
-        }
+        // SH -> RGB is evaluated by sh_forward_kernel (sh.cu) on the Gaussians this kernel keeps (radii > 0)
+        (void)has_colors; (void)shs; (void)rgb; (void)clamped; (void)D; (void)M;
         float opa = __ldg(opacities + idx);
         GeomRec g;
         g.tu = make_float4(Tu.x, Tu.y, Tu.z, cx);
@@ -208,10 +205,9 @@ surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
     const bool visible = radii[idx] > 0;
     float view[16];
     load16(vc.view, view);
-    if (dL_dsh != nullptr) {
-        float* o = dL_dsh + (size_t)idx * M * 3;
-        for (int j = 0; j < 3 * M; j++) o[j] = 0.f;
-    }
+    // dL/dsh and the view-direction term of dL/dmean3D are produced by sh_backward_kernel (sh.cu), which runs
+    // after this kernel and accumulates into dL_dmean3D
+    (void)dL_dsh; (void)shs; (void)clamped; (void)D; (void)M;
     if (visible) {
         GeomRec g = geom[idx];
         {   // moments of dL/dp -> dL/dT (the linear part of S/backward.cu:413-421, once per Gaussian)
@@ -316,19 +312,6 @@ surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
                             make_float3(dRS1.x * sc.y, dRS1.y * sc.y, dRS1.z * sc.y), dtn);
             dscale = make_float2(dot3(dRS0, c0), dot3(dRS1, c1));
             dmean = make_float3(dM[2][0], dM[2][1], dM[2][2]);
-            if (shs != nullptr) {
-                float3 dm = sh_to_rgb_bwd(D, M, p, make_float3(__ldg(vc.campos), __ldg(vc.campos + 1), __ldg(vc.campos + 2)),
-                                          shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx, dcol,
-                                          dL_dsh + (size_t)idx * M * 3);
-                dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
-            }
-        } else if (shs != nullptr) {
-            // precomputed transMat with SH colours: S/backward.cu:630-631 still runs
-            p = make_float3(__ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1), __ldg(means3D + 3 * idx + 2));
-            float3 dm = sh_to_rgb_bwd(D, M, p, make_float3(__ldg(vc.campos), __ldg(vc.campos + 1), __ldg(vc.campos + 2)),
-                                      shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx, dcol,
-                                      dL_dsh + (size_t)idx * M * 3);
-            dmean = dm;
         }
         // densification hack, S/backward.cu:633-636: uses the stored dL_dtransMat and T[8]
         float depth = g.tw.z;
