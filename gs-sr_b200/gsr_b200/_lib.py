@@ -65,6 +65,12 @@ def lib():
     L.gsr_tsdf_fuse.restype = C.c_int
     L.gsr_tsdf_fuse.argtypes = [C.c_longlong, _fp, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, _fp,
                                 C.c_int, _fp, _fp, _fp, C.c_void_p]
+    L.gsr_ssim_tile_count.restype = C.c_size_t
+    L.gsr_ssim_tile_count.argtypes = [C.c_int] * 3
+    L.gsr_ssim_forward.restype = C.c_int
+    L.gsr_ssim_forward.argtypes = [C.c_int] * 3 + [_fp, _fp, C.POINTER(C.c_float)] + [_fp] * 4 + [C.c_void_p]
+    L.gsr_ssim_backward.restype = C.c_int
+    L.gsr_ssim_backward.argtypes = [C.c_int] * 3 + [_fp, _fp, C.POINTER(C.c_float)] + [_fp] * 5 + [C.c_void_p]
     _LIB = L
     return L
 

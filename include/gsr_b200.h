@@ -250,6 +250,25 @@ int gsr_tsdf_fuse(long long n, const float* samples, int contracted, const float
                   float radius, float voxel_size, int nviews, const gsr_tsdf_view* views, int init,
                   float* tsdf, float* weights, float* rgb, void* stream);
 
+/* ---- fused SSIM loss (image-space step right after the rasterizer) ---------------------- */
+
+/* Replaces VanillaScene._ssim / .ssim (gssr/scene/vanilla_scene.py:32-61): five depthwise 11x11
+ * conv2d + elementwise map in the forward, autograd's three more convolutions in the backward.
+ * img1 / img2: (channels, height, width) device arrays; window11: HOST array with the 11 taps of the
+ * normalised 1-D Gaussian (the reference's _gaussian(11, 1.5)); the 2-D window is their outer product.
+ * Forward writes three derivative maps (same shape as img1: d ssim/d(G*x), d ssim/d(G*x^2), d ssim/d(G*xy))
+ * for the backward and one partial sum of the SSIM map per CTA tile into tile_sums
+ * (gsr_ssim_tile_count(...) floats); ssim.mean() = sum(tile_sums) / (channels*height*width).
+ * Backward: dL_dimg1 = upstream * d ssim.mean()/d img1, upstream_dev = DEVICE scalar (autograd's
+ * grad_output), so the call never synchronises. */
+size_t gsr_ssim_tile_count(int channels, int height, int width);
+int gsr_ssim_forward(int channels, int height, int width, const float* img1, const float* img2,
+                     const float* window11_host, float* dmu1, float* dE11, float* dE12, float* tile_sums,
+                     void* stream);
+int gsr_ssim_backward(int channels, int height, int width, const float* img1, const float* img2,
+                      const float* window11_host, const float* dmu1, const float* dE11, const float* dE12,
+                      const float* upstream_dev, float* dL_dimg1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

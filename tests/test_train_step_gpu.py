@@ -83,3 +83,17 @@ def test_pgsr_iteration_matches_reference_kernels():
         la, _ = a.step()
         lb, _ = b.step()
     assert abs(la - lb) <= 2e-3 * abs(lb), (la, lb)
+
+
+def test_fused_ssim_in_the_training_iteration():
+    """Swapping VanillaScene.ssim for gsr_b200.ssim leaves the iteration's losses and statistics unchanged."""
+    from train_harness import MiniTwoDGSTrainer
+    kw = dict(P=20000, W=256, H=192, seed=5, lambda_dist=100.0, impl="ours")
+    a, b = MiniTwoDGSTrainer(**kw), MiniTwoDGSTrainer(**kw)
+    a.fused_ssim = True
+    la, da = a.step()
+    lb, db = b.step()
+    for k in da:
+        assert abs(da[k] - db[k]) <= 1e-5 * max(abs(db[k]), 1e-3), (k, da[k], db[k])
+    ga, gb = a.xyz_gradient_accum.double(), b.xyz_gradient_accum.double()
+    assert float((ga - gb).norm() / gb.norm()) <= 1e-4

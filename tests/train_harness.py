@@ -140,7 +140,12 @@ class MiniTwoDGSTrainer:
         return output
 
     # ---- vanilla_scene.py:29-69, twodgs_scene.py:25-35 ----------------------------------------------------
+    fused_ssim = False      # True: gsr_b200.ssim (fused kernel) instead of the reference's conv2d formulation
+
     def ssim(self, img1, img2):
+        if self.fused_ssim:
+            from gsr_b200.ssim import ssim as fused
+            return fused(img1, img2)
         w, pad = self.window, 5
         mu1, mu2 = F.conv2d(img1, w, padding=pad, groups=3), F.conv2d(img2, w, padding=pad, groups=3)
         mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
@@ -433,13 +438,15 @@ class MiniPGSRTrainer(MiniTwoDGSTrainer):
         return loss_value, {k_: float(v.detach()) for k_, v in losses.items()}
 
 
-def measure_iters_per_s(impl, P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, scaffold=False, pgsr=False):
+def measure_iters_per_s(impl, P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, scaffold=False, pgsr=False,
+                        fused_ssim=False):
     if pgsr:
         tr = MiniPGSRTrainer(P, W=W, H=H, seed=seed, impl=impl)
     elif scaffold:
         tr = MiniScaffold2DGSTrainer(P, W=W, H=H, seed=seed, impl=impl)
     else:
         tr = MiniTwoDGSTrainer(P, W, H, seed=seed, impl=impl)
+    tr.fused_ssim = fused_ssim
     for _ in range(warmup):
         tr.step()
     torch.cuda.synchronize()
