@@ -31,6 +31,8 @@ __global__ void surfel_render_fwd(const uint32_t*, const float4*, size_t, int, i
                                   uint32_t*, float*, float*);
 __global__ void surfel_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*,
                                   const float*, const uint32_t*, const float*, const float*, float*);
+int bwd_ctas_per_tile();
+int fwd_ctas_per_tile();
 template <bool kRadiiOnly>
 __global__ void ewa_preprocess_fwd(int, int, int, const float*, const float*, const float4*, const float*, const float*,
                                    const float*, const bool, const ViewParams, const float, const float, const float,
@@ -311,7 +313,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         GSR_CUDA_CHECK(cudaGetLastError());
     }
     prof_begin(GSR_PROF_RENDER_FWD, s);
-    surfel_render_fwd<<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
+    surfel_render_fwd<<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
                                                   iw.final_T, iw.n_contrib, out_color, out_others);
     prof_end(GSR_PROF_RENDER_FWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
@@ -353,7 +355,7 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
     GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * GACC_STRIDE * sizeof(float), s));
     if (R > 0) {
         prof_begin(GSR_PROF_RENDER_BWD, s);
-        surfel_render_bwd<<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
+        surfel_render_bwd<<<ntiles * bwd_ctas_per_tile(), 256 / bwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
                                                       iw.final_T, iw.n_contrib, dL_dpix, dL_dothers,
                                                       bw.gacc);
         prof_end(GSR_PROF_RENDER_BWD, s);

@@ -26,7 +26,8 @@ __device__ __forceinline__ float fast_ex2(float x) {
 
 // One thread: arm the stage's mbarrier and launch the six plane copies of entries
 // [first, first+count) of this tile's list.
-__device__ __forceinline__ void issue_batch(float4 (*dst)[RBATCH], const float4* __restrict__ src, size_t pstride,
+template <int NB>
+__device__ __forceinline__ void issue_batch(float4 (*dst)[NB], const float4* __restrict__ src, size_t pstride,
                                             int first, int count, uint64_t* bar) {
     const uint32_t bytes = (uint32_t)count * 16u;
     mbar_expect_tx(bar, bytes * REC_PLANES);

@@ -7,8 +7,11 @@
 // branch :403-433 and the low-pass branch :434-441).
 //
 // B200 design:
-//   * same CTA/warp/pixel mapping, cp.async.bulk staging and exact warp-block culling as
-//     the forward; the walk starts at the tile's last needed batch (max last_contributor);
+//   * same warp/pixel mapping (8x4 pixels per warp), cp.async.bulk staging and exact warp-block
+//     culling as the forward, but one CTA = 4 warps = HALF a tile (16x8 pixels; two CTAs per
+//     tile walk the same list) and the warps of a CTA are decoupled: a 3-stage ring whose
+//     stages are refilled by whichever warp arrives last, no __syncthreads() in the walk;
+//     the walk starts at the half tile's last needed batch (max last_contributor);
 //   * geometry gradients are accumulated as MOMENTS of dL/dp (p = a x + b y + c, the
 //     adjugate-form intersection): M0 = sum dp, MX = sum x~ dp, MY = sum y~ dp with (x~, y~)
 //     measured from the splat's rounded screen centre, plus dL/d det(T).  The cross products
@@ -71,18 +74,37 @@ __device__ __forceinline__ float warp_sum(float x) {
     return x;
 }
 
-__global__ void __launch_bounds__(TILE_PIX, 3)
+#ifndef GSR_BWD_BATCH
+#define GSR_BWD_BATCH 128
+#define GSR_BWD_STAGES 3
+#endif
+constexpr int BWD_BATCH = GSR_BWD_BATCH;      // record entries per ring stage
+constexpr int BWD_STAGES = GSR_BWD_STAGES;
+#ifndef GSR_BWD_WARPS
+#define GSR_BWD_WARPS 4   // measured on cfg-B (B200): 8 warps 3.18 ms, 4 warps 3.08 ms, 2 warps 3.23 ms
+#endif
+constexpr int BWD_WARPS = GSR_BWD_WARPS;      // warps per CTA: 8 = whole 16x16 tile, 4 = half tile (16x8), 2 = 16x4 strip
+constexpr int BWD_SPLIT = 8 / BWD_WARPS;      // CTAs per tile
+constexpr int BWD_MINB = BWD_WARPS == 8 ? 3 : (BWD_WARPS == 4 ? 6 : 12);
+
+__global__ void __launch_bounds__(BWD_WARPS * 32, BWD_MINB)
 surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, const float* __restrict__ final_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
                   const float* __restrict__ dL_dothers, float* __restrict__ gacc) {
-    __shared__ __align__(128) float4 sbuf[2][REC_PLANES][RBATCH];
-    __shared__ __align__(8) uint64_t full_bar[2];
+    // BWD_STAGES-deep ring of record batches.  Warps are NOT synchronised per batch: every warp waits on the
+    // stage's full barrier, consumes (or skips) the batch and then arrives on the stage's counter; the warp whose
+    // arrival is the 8th re-arms the barrier and issues the bulk copy of the batch BWD_STAGES ahead into the freed
+    // stage.  A fast warp can therefore run up to BWD_STAGES batches ahead of the slowest one instead of idling at
+    // a CTA barrier after every 128 entries (barrier stalls were 25 % of all warp time with __syncthreads()).
+    __shared__ __align__(128) float4 sbuf[BWD_STAGES][REC_PLANES][BWD_BATCH];
+    __shared__ __align__(8) uint64_t full_bar[BWD_STAGES];
+    __shared__ int s_arrive[BWD_STAGES];
     __shared__ int s_maxlast;
 
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x / BWD_SPLIT;
     const int tx = tile % gx, ty = tile / gx;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (threadIdx.x >> 5) + (blockIdx.x % BWD_SPLIT) * BWD_WARPS, lane = threadIdx.x & 31;
     const int wx0 = (warp & 1) * 8, wy0 = (warp >> 1) * 4;
     const int lx = wx0 + (lane & 7), ly = wy0 + (lane >> 3);
     const int px = tx * TILE + lx, py = ty * TILE + ly;
@@ -102,8 +124,8 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     const int wlast = __reduce_max_sync(FULLMASK, last);
     if (threadIdx.x == 0) {
         s_maxlast = 0;
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
+#pragma unroll
+        for (int i = 0; i < BWD_STAGES; i++) { mbar_init(&full_bar[i], 1); s_arrive[i] = 0; }
         mbar_fence_init();
     }
     __syncthreads();
@@ -111,13 +133,13 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     __syncthreads();
     const int maxlast = min(s_maxlast, n);
     if (maxlast <= 0) return;
-    const int nb = (maxlast + RBATCH - 1) / RBATCH;  // batches [0, nb), walked from nb-1 down
+    const int nb = (maxlast + BWD_BATCH - 1) / BWD_BATCH;  // batches [0, nb), walked from nb-1 down
 
-    auto batch_count = [&](int b) { return min(RBATCH, n - b * RBATCH); };
+    auto batch_count = [&](int b) { return min(BWD_BATCH, n - b * BWD_BATCH); };
     if (threadIdx.x == 0)
-        for (int i = 0; i < 2 && nb - 1 - i >= 0; i++) {
+        for (int i = 0; i < BWD_STAGES && nb - 1 - i >= 0; i++) {
             const int b = nb - 1 - i;
-            issue_batch(sbuf[i], src, pstride, b * RBATCH, batch_count(b), &full_bar[i]);
+            issue_batch(sbuf[i], src, pstride, b * BWD_BATCH, batch_count(b), &full_bar[i]);
         }
 
     // per-pixel constants
@@ -146,15 +168,15 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     float last_depth = 0.f, accum_depth_rec = 0.f, accum_alpha_rec = 0.f;
     float ln0 = 0.f, ln1 = 0.f, ln2 = 0.f, an0 = 0.f, an1 = 0.f, an2 = 0.f, last_dL_dT = 0.f;
 
+    int stage = 0;
+    uint32_t parity = 0;
     for (int it = 0; it < nb; it++) {
         const int b = nb - 1 - it;
-        const int stage = it & 1;
-        const uint32_t parity = (uint32_t)((it >> 1) & 1);
         const int cnt = batch_count(b);
-        const int base = b * RBATCH;
+        const int base = b * BWD_BATCH;
+        mbar_wait(&full_bar[stage], parity);
         if (base < wlast) {
-            mbar_wait(&full_bar[stage], parity);
-            const float4(*sb)[RBATCH] = sbuf[stage];
+            const float4(*sb)[BWD_BATCH] = sbuf[stage];
             for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
                 if (base + c0 >= wlast) continue;
                 const int e = c0 + lane;
@@ -250,13 +272,22 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 }
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && it + 2 < nb) {
-            const int b2 = nb - 1 - (it + 2);
-            fence_proxy_async();
-            issue_batch(sbuf[stage], src, pstride, b2 * RBATCH, batch_count(b2), &full_bar[stage]);
+        // release the stage; the last of the 8 warps to arrive refills it with the batch BWD_STAGES ahead
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            const int old = atomicAdd(&s_arrive[stage], 1);
+            if ((old & (BWD_WARPS - 1)) == BWD_WARPS - 1 && it + BWD_STAGES < nb) {
+                __threadfence_block();
+                fence_proxy_async();
+                const int b2 = nb - 1 - (it + BWD_STAGES);
+                issue_batch(sbuf[stage], src, pstride, b2 * BWD_BATCH, batch_count(b2), &full_bar[stage]);
+            }
         }
+        if (++stage == BWD_STAGES) { stage = 0; parity ^= 1u; }
     }
 }
+
+int bwd_ctas_per_tile() { return BWD_SPLIT; }
 
 }  // namespace gsr

@@ -27,7 +27,13 @@
 
 namespace gsr {
 
-__global__ void __launch_bounds__(TILE_PIX)
+#ifndef GSR_FWD_WARPS
+#define GSR_FWD_WARPS 8
+#endif
+constexpr int FWD_WARPS = GSR_FWD_WARPS;      // warps per CTA: 8 = whole 16x16 tile, 4 = half tile (16x8)
+constexpr int FWD_SPLIT = 8 / FWD_WARPS;
+
+__global__ void __launch_bounds__(FWD_WARPS * 32)
 surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, float* __restrict__ final_T,
                   uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
@@ -35,9 +41,9 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     __shared__ __align__(128) float4 sbuf[2][REC_PLANES][RBATCH];
     __shared__ __align__(8) uint64_t full_bar[2];
 
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x / FWD_SPLIT;
     const int tx = tile % gx, ty = tile / gx;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (threadIdx.x >> 5) + (blockIdx.x % FWD_SPLIT) * FWD_WARPS, lane = threadIdx.x & 31;
     const int wx0 = (warp & 1) * 8, wy0 = (warp >> 1) * 4;
     const int lx = wx0 + (lane & 7), ly = wy0 + (lane >> 3);
     const int px = tx * TILE + lx, py = ty * TILE + ly;
@@ -155,5 +161,7 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
         out_others[pid + 10 * N] = mn2;
     }
 }
+
+int fwd_ctas_per_tile() { return FWD_SPLIT; }
 
 }  // namespace gsr

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "libgsr_b200.so")
+# GSR_B200_LIB: developer hook to A/B another build of the same library (never a fallback: it must exist)
+LIB_PATH = os.environ.get("GSR_B200_LIB") or os.path.join(_PKG_ROOT, "libgsr_b200.so")
 
 BUFFER_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 _fp = C.c_void_p  # device pointers travel as integers
