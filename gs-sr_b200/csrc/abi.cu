@@ -33,6 +33,7 @@ __global__ void surfel_render_bwd(const uint32_t*, const float4*, size_t, int, i
                                   const float*, const uint32_t*, const float*, const float*, float*);
 int bwd_ctas_per_tile();
 int fwd_ctas_per_tile();
+int ewa_bwd_ctas_per_tile();
 template <bool kRadiiOnly>
 __global__ void ewa_preprocess_fwd(int, int, int, const float*, const float*, const float4*, const float*, const float*,
                                    const float*, const bool, const ViewParams, const float, const float, const float,
@@ -565,14 +566,14 @@ static int ewa_backward(const EwaBwdArgs& a, const char* who) {
     if (R > 0) {
         prof_begin(GSR_PROF_RENDER_BWD, s);
         if (a.geo)
-            ewa_render_bwd<2><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+            ewa_render_bwd<2><<<ntiles * ewa_bwd_ctas_per_tile(), 256 / ewa_bwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
                                                           iw.final_T, iw.n_contrib, a.all_map_pixels, a.dL_dpix, a.dL_dout_all_map,
                                                           a.dL_dout_plane_depth, bw.gacc);
         else if (a.plane)
-            ewa_render_bwd<1><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+            ewa_render_bwd<1><<<ntiles * ewa_bwd_ctas_per_tile(), 256 / ewa_bwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
                                                           iw.final_T, iw.n_contrib, nullptr, a.dL_dpix, nullptr, nullptr, bw.gacc);
         else
-            ewa_render_bwd<0><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+            ewa_render_bwd<0><<<ntiles * ewa_bwd_ctas_per_tile(), 256 / ewa_bwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
                                                           iw.final_T, iw.n_contrib, nullptr, a.dL_dpix, nullptr, nullptr, bw.gacc);
         prof_end(GSR_PROF_RENDER_BWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());

@@ -255,8 +255,13 @@ __device__ __forceinline__ float ewa_reduce16(float (&v)[16], int lane) {
 }
 
 // MODE 0: 3DGS (9 sums)   1: plane without render_geo (+ |dL_dmean2D|, 11 sums)   2: plane with render_geo (16 sums)
+// CTA = 4 warps = half a tile (16x8 px), 3-stage record ring, warps decoupled (the last warp to arrive on a stage
+// refills it; no __syncthreads() in the walk) -- same scheme as surfel_render_bwd.cu.
+constexpr int EWA_BWD_WARPS = 4, EWA_BWD_SPLIT = 8 / EWA_BWD_WARPS, EWA_BWD_STAGES = 3;
+int ewa_bwd_ctas_per_tile() { return EWA_BWD_SPLIT; }
+
 template <int MODE>
-__global__ void __launch_bounds__(TILE_PIX, 3)
+__global__ void __launch_bounds__(EWA_BWD_WARPS * 32, 6)
 ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W, int H,
                int gx, const float* __restrict__ bg, float focal_x, float focal_y, const float* __restrict__ final_T,
                const uint32_t* __restrict__ n_contrib, const float* __restrict__ all_map_pixels,
@@ -265,13 +270,14 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
     constexpr bool GEO = MODE == 2;
     constexpr int NPL = GEO ? EWA_PLANES_GEO : EWA_PLANES;
     constexpr int NV = MODE == 0 ? 9 : (MODE == 1 ? 11 : 16);
-    __shared__ __align__(128) float4 sbuf[2][NPL][RBATCH];
-    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ __align__(128) float4 sbuf[EWA_BWD_STAGES][NPL][RBATCH];
+    __shared__ __align__(8) uint64_t full_bar[EWA_BWD_STAGES];
+    __shared__ int s_arrive[EWA_BWD_STAGES];
     __shared__ int s_maxlast;
 
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x / EWA_BWD_SPLIT;
     const int tx = tile % gx, ty = tile / gx;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (threadIdx.x >> 5) + (blockIdx.x % EWA_BWD_SPLIT) * EWA_BWD_WARPS, lane = threadIdx.x & 31;
     const int wx0 = (warp & 1) * 8, wy0 = (warp >> 1) * 4;
     const int lx = wx0 + (lane & 7), ly = wy0 + (lane >> 3);
     const int px = tx * TILE + lx, py = ty * TILE + ly;
@@ -290,8 +296,8 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
     const int wlast = __reduce_max_sync(FULLMASK, last);
     if (threadIdx.x == 0) {
         s_maxlast = 0;
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
+#pragma unroll
+        for (int i = 0; i < EWA_BWD_STAGES; i++) { mbar_init(&full_bar[i], 1); s_arrive[i] = 0; }
         mbar_fence_init();
     }
     __syncthreads();
@@ -303,7 +309,7 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
 
     auto batch_count = [&](int b) { return min(RBATCH, n - b * RBATCH); };
     if (threadIdx.x == 0)
-        for (int i = 0; i < 2 && nb - 1 - i >= 0; i++) {
+        for (int i = 0; i < EWA_BWD_STAGES && nb - 1 - i >= 0; i++) {
             const int b = nb - 1 - i;
             ewa_issue_batch<NPL>(sbuf[i], src, pstride, b * RBATCH, batch_count(b), &full_bar[i]);
         }
@@ -335,14 +341,14 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;
     float lm0 = 0.f, lm1 = 0.f, lm2 = 0.f, lm3 = 0.f, lm4 = 0.f, am0 = 0.f, am1 = 0.f, am2 = 0.f, am3 = 0.f, am4 = 0.f;
 
+    int stage = 0;
+    uint32_t parity = 0;
     for (int it = 0; it < nb; it++) {
         const int b = nb - 1 - it;
-        const int stage = it & 1;
-        const uint32_t parity = (uint32_t)((it >> 1) & 1);
         const int cnt = batch_count(b);
         const int base = b * RBATCH;
+        mbar_wait(&full_bar[stage], parity);
         if (base < wlast) {
-            mbar_wait(&full_bar[stage], parity);
             const float4(*sb)[RBATCH] = sbuf[stage];
             for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
                 if (base + c0 >= wlast) continue;
@@ -408,12 +414,18 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                 }
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && it + 2 < nb) {
-            const int b2 = nb - 1 - (it + 2);
-            fence_proxy_async();
-            ewa_issue_batch<NPL>(sbuf[stage], src, pstride, b2 * RBATCH, batch_count(b2), &full_bar[stage]);
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            const int old = atomicAdd(&s_arrive[stage], 1);
+            if ((old & (EWA_BWD_WARPS - 1)) == EWA_BWD_WARPS - 1 && it + EWA_BWD_STAGES < nb) {
+                __threadfence_block();
+                fence_proxy_async();
+                const int b2 = nb - 1 - (it + EWA_BWD_STAGES);
+                ewa_issue_batch<NPL>(sbuf[stage], src, pstride, b2 * RBATCH, batch_count(b2), &full_bar[stage]);
+            }
         }
+        if (++stage == EWA_BWD_STAGES) { stage = 0; parity ^= 1u; }
     }
 }
 template __global__ void ewa_render_bwd<0>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,

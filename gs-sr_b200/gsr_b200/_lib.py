@@ -72,6 +72,10 @@ def lib():
     L.gsr_ssim_forward.argtypes = [C.c_int] * 3 + [_fp, _fp, C.POINTER(C.c_float)] + [_fp] * 4 + [C.c_void_p]
     L.gsr_ssim_backward.restype = C.c_int
     L.gsr_ssim_backward.argtypes = [C.c_int] * 3 + [_fp, _fp, C.POINTER(C.c_float)] + [_fp] * 5 + [C.c_void_p]
+    L.gsr_surfel_post_forward.restype = C.c_int
+    L.gsr_surfel_post_forward.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float, _fp, _fp, _fp, C.c_void_p]
+    L.gsr_surfel_post_backward.restype = C.c_int
+    L.gsr_surfel_post_backward.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float] + [_fp] * 6 + [C.c_void_p]
     _LIB = L
     return L
 

@@ -269,6 +269,22 @@ int gsr_ssim_backward(int channels, int height, int width, const float* img1, co
                       const float* window11_host, const float* dmu1, const float* dE11, const float* dE12,
                       const float* upstream_dev, float* dL_dimg1, void* stream);
 
+/* ---- fused allmap post-processing of the 2DGS scene (image-space step after the rasterizer) -- */
+
+/* Replaces the torch block of TwoDGSScene.render after the rasterizer call
+ * (gssr/scene/twodgs_scene.py:88-117) including depth_to_normal / depths_to_points
+ * (gssr/utils/point_utils.py:9-37).  allmap: (11,H,W) as returned by the surfel rasterizer.
+ * cam21: DEVICE array of 21 floats = K (3x3 row-major, rays_d = [x y 1] @ K with
+ * K = intrins.inverse().T @ c2w[:3,:3].T), rays_o (3), R = world_view_transform[:3,:3] (3x3 row-major).
+ * Forward writes render_normal (3,H,W; world space), surf_depth (1,H,W), surf_normal (3,H,W; times the
+ * detached alpha, zero on the border).  Backward takes upstream gradients on those three outputs (any may be
+ * NULL = zero), needs scratch6 = 6*H*W floats, and fully writes dL_dallmap (11,H,W). */
+int gsr_surfel_post_forward(int height, int width, const float* allmap, const float* cam21, float depth_ratio,
+                            float* render_normal, float* surf_depth, float* surf_normal, void* stream);
+int gsr_surfel_post_backward(int height, int width, const float* allmap, const float* cam21, float depth_ratio,
+                             const float* surf_depth, const float* g_render_normal, const float* g_surf_depth,
+                             const float* g_surf_normal, float* scratch6, float* dL_dallmap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,8 @@ from oracle import refcuda
 for P, W, H, it in ((100_000, 800, 800, 40), (2_000_000, 1600, 1060, 12)):
     a, _ = measure_iters_per_s("ours", P, W, H, iters=it)
     af, _ = measure_iters_per_s("ours", P, W, H, iters=it, fused_ssim=True)
-    msg = f"P={P} {W}x{H} SH3: ours {a:.1f} it/s (+ fused SSIM {af:.1f} it/s)"
+    ap, _ = measure_iters_per_s("ours", P, W, H, iters=it, fused_ssim=True, fused_post=True)
+    msg = f"P={P} {W}x{H} SH3: ours {a:.1f} it/s (+ fused SSIM {af:.1f}, + fused post-processing {ap:.1f} it/s)"
     if refcuda.available("surfel"):
         b, _ = measure_iters_per_s("reference", P, W, H, iters=it)
         msg += f", reference kernels {b:.1f} it/s, x{a/b:.2f}"

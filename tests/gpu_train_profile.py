@@ -4,9 +4,15 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import harness  # noqa
 import torch
 from torch.profiler import profile, ProfilerActivity
-from train_harness import MiniTwoDGSTrainer
+from train_harness import MiniTwoDGSTrainer, MiniScaffold2DGSTrainer, MiniPGSRTrainer
+flow = sys.argv[4] if len(sys.argv) > 4 else "2dgs"
 P, W, H = (int(x) for x in (sys.argv[1:4] or (2_000_000, 1600, 1060)))
-tr = MiniTwoDGSTrainer(P, W, H, impl="ours", lambda_dist=0.0)
+if flow == "scaffold":
+    tr = MiniScaffold2DGSTrainer(P, W=W, H=H, impl="ours")
+elif flow == "pgsr":
+    tr = MiniPGSRTrainer(P, W=W, H=H, impl="ours")
+else:
+    tr = MiniTwoDGSTrainer(P, W, H, impl="ours", lambda_dist=0.0)
 for _ in range(5): tr.step()
 torch.cuda.synchronize()
 N = 5

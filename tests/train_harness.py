@@ -109,6 +109,11 @@ class MiniTwoDGSTrainer:
         else:
             rendered_image, radii, allmap = _RefSurfelFn.apply(means3D, screenspace_points, shs, None, opacity, scales,
                                                                rotations, self.ref, rs)
+        if self.fused_post:
+            from gsr_b200.surfel_post import surfel_postprocess
+            post = surfel_postprocess(allmap, self.view, self.proj, depth_ratio=self.depth_ratio)
+            return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+                    "radii": radii, **post}
         render_alpha = allmap[1:2]
         render_normal = allmap[2:5]
         render_normal = (render_normal.permute(1, 2, 0) @ (self.view[:3, :3].T)).permute(2, 0, 1)
@@ -141,6 +146,7 @@ class MiniTwoDGSTrainer:
 
     # ---- vanilla_scene.py:29-69, twodgs_scene.py:25-35 ----------------------------------------------------
     fused_ssim = False      # True: gsr_b200.ssim (fused kernel) instead of the reference's conv2d formulation
+    fused_post = False      # True: gsr_b200.surfel_post (fused kernels) instead of the torch post-processing block
 
     def ssim(self, img1, img2):
         if self.fused_ssim:
@@ -439,14 +445,14 @@ class MiniPGSRTrainer(MiniTwoDGSTrainer):
 
 
 def measure_iters_per_s(impl, P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, scaffold=False, pgsr=False,
-                        fused_ssim=False):
+                        fused_ssim=False, fused_post=False):
     if pgsr:
         tr = MiniPGSRTrainer(P, W=W, H=H, seed=seed, impl=impl)
     elif scaffold:
         tr = MiniScaffold2DGSTrainer(P, W=W, H=H, seed=seed, impl=impl)
     else:
         tr = MiniTwoDGSTrainer(P, W, H, seed=seed, impl=impl)
-    tr.fused_ssim = fused_ssim
+    tr.fused_ssim, tr.fused_post = fused_ssim, fused_post
     for _ in range(warmup):
         tr.step()
     torch.cuda.synchronize()
