@@ -327,6 +327,22 @@ def cpu_oracle_sample(P, W, H, stride=4):
                 R=f["num_rendered"])
 
 
+def train_iters(impl):
+    """Second half of BASELINE's metric ("train iters/s") on BASELINE config 2 (cfg-A: 2DGS, 100k surfels, 800x800, SH 3):
+    the GS-SR-style iteration of tests/train_harness.py (render + post-processing + L1/SSIM/normal/dist losses + backward +
+    densification statistics + Adam, loss.item() every step).  Our arm uses the drop-in rasterizer and the fused SSIM /
+    post-processing ops; the reference arm uses the unmodified reference kernels and the reference's torch ops."""
+    from train_harness import measure_iters_per_s
+    ours = impl == "ours"
+    v, _ = measure_iters_per_s("ours" if ours else "reference", 100_000, 800, 800, iters=40, warmup=5,
+                               fused_ssim=ours, fused_post=ours)
+    return {"metric": "train iters/s", "value": v, "unit": "iters/s",
+            "workload": "2DGS iteration, P=100000 synthetic surfels, 800x800, SH degree 3 (BASELINE config 2), Adam, "
+                        "loss.item() per step; tests/train_harness.py",
+            "ops": "drop-in rasterizer + fused SSIM + fused post-processing" if ours else
+                   "reference CUDA rasterizer + reference torch ops"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,6 +353,7 @@ def main():
     ap.add_argument("--W", type=int, default=W_DEFAULT)
     ap.add_argument("--H", type=int, default=H_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -373,6 +390,8 @@ def main():
                                                         "kernels (diff-surfel-rasterization compiled for sm_100a "
                                                         "by oracle/build_ref.sh) on the full workload on the GPU"},
                              "stats": {"num_rendered": r["R"], "visible": r["V"]}, "gpu_launches": 0})
+                if world == 1 and not args.no_train:
+                    base["train"] = train_iters("reference")
                 print(json.dumps(base))
         else:
             if rank == 0:
@@ -413,6 +432,8 @@ def main():
             "kernel_ms": r["kernel_ms"],
             "stats": {"num_rendered": R, "visible": r["V"], "pixels": N, "checksum": r["checksum"]},
         })
+        if world == 1 and not args.no_train:
+            base["train"] = train_iters("ours")
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_oracle_sample(args.P, args.W, args.H)
             base["cpu_baseline"] = {"value": c["value"], "unit": "Gaussians/s", "cores": c["cores"], "kind": "port",
