@@ -286,6 +286,14 @@ __device__ __forceinline__ float box_gap2(float3 amin, float3 amax, float4 bmin,
     return (gx * gx + gy * gy + gz * gz) * 0.9999f;
 }
 
+// squared distance from a point to a box, deflated like box_gap2
+__device__ __forceinline__ float point_box_gap2(float3 p, float4 bmin, float4 bmax) {
+    const float gx = fmaxf(fmaxf(bmin.x - p.x, p.x - bmax.x), 0.f);
+    const float gy = fmaxf(fmaxf(bmin.y - p.y, p.y - bmax.y), 0.f);
+    const float gz = fmaxf(fmaxf(bmin.z - p.z, p.z - bmax.z), 0.f);
+    return (gx * gx + gy * gy + gz * gz) * 0.9999f;
+}
+
 __global__ void __launch_bounds__(256) knn_query(int P, const float4* __restrict__ spts, const KnnLevels lv,
                                                  float* __restrict__ out) {
     const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -328,10 +336,14 @@ __global__ void __launch_bounds__(256) knn_query(int P, const float4* __restrict
         mask &= mask - 1;
         const int level = st_level[sp - 1];
         const int node = st_first[sp - 1] + bit;
-        // the bound may have shrunk since this node was queued: test again (one broadcast load)
+        // Exact per-query test when the node is popped (one broadcast load): the node is needed only if SOME lane's
+        // own point is closer to its box than that lane's current 3rd-best distance.  The box-to-box test used when
+        // children are queued is conservative but useless for a leaf whose 32 Morton-consecutive points straddle a jump
+        // of the curve (its box spans the scene and touches everything); those leaves used to walk most of the tree
+        // and set the kernel time (15 ms at 1 M uniform points).
         {
             const float4 mn = lv.box[level][2 * (size_t)node], mx = lv.box[level][2 * (size_t)node + 1];
-            if (box_gap2(amin, amax, mn, mx) > bound) continue;
+            if (!__any_sync(FULL, have && !(point_box_gap2(ref, mn, mx) > b2))) continue;
         }
         if (level == 0) {
             if (node == leaf) continue;   // seeded above
