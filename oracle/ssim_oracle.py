@@ -38,4 +38,4 @@ def ssim_value_and_grad(img1_np, img2_np, dtype=torch.float32):
     y = torch.from_numpy(img2_np).to(dtype)
     v = ssim(x, y)
     v.backward()
-    return float(v), x.grad.numpy()
+    return float(v.detach()), x.grad.numpy()
