@@ -16,13 +16,15 @@ for P, W, H, it in ((100_000, 800, 800, 40), (2_000_000, 1600, 1060, 12)):
     print(msg)
 for N in (400_000,):
     a, _ = measure_iters_per_s("ours", N, 1600, 1060, iters=12, scaffold=True)
-    msg = f"Scaffold-2DGS flow, {N} anchors x5 offsets, 1600x1060: ours {a:.1f} it/s"
+    af, _ = measure_iters_per_s("ours", N, 1600, 1060, iters=12, scaffold=True, fused_ssim=True, fused_post=True)
+    msg = f"Scaffold-2DGS flow, {N} anchors x5 offsets, 1600x1060: ours {a:.1f} it/s (+ fused SSIM and post-processing {af:.1f} it/s)"
     if refcuda.available("surfel"):
         b, _ = measure_iters_per_s("reference", N, 1600, 1060, iters=12, scaffold=True)
         msg += f", reference kernels {b:.1f} it/s, x{a/b:.2f}"
     print(msg)
 a, _ = measure_iters_per_s("ours", 1_000_000, 1600, 900, iters=12, pgsr=True)
-msg = f"PGSR flow (2 views/iter), P=1M, 1600x900: ours {a:.1f} it/s"
+af, _ = measure_iters_per_s("ours", 1_000_000, 1600, 900, iters=12, pgsr=True, fused_ssim=True)
+msg = f"PGSR flow (2 views/iter), P=1M, 1600x900: ours {a:.1f} it/s (+ fused SSIM {af:.1f} it/s)"
 if refcuda.available("plane"):
     b, _ = measure_iters_per_s("reference", 1_000_000, 1600, 900, iters=12, pgsr=True)
     msg += f", reference kernels {b:.1f} it/s, x{a/b:.2f}"

@@ -282,11 +282,15 @@ class MiniScaffold2DGSTrainer(MiniTwoDGSTrainer):
                 scales=scaling, rotations=rot, cov3D_precomp=None)
         else:
             image, radii, allmap = _RefSurfelFn.apply(xyz, screenspace_points, None, color, opacity, scaling, rot, self.ref, rs)
-        render_alpha = allmap[1:2]
-        render_normal = (allmap[2:5].permute(1, 2, 0) @ (self.view[:3, :3].T)).permute(2, 0, 1)
-        depth = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
-        surf_normal = self.depth_to_normal(depth).permute(2, 0, 1) * render_alpha.detach()
-        out = {"render": image, "normal": render_normal, "surf_normal": surf_normal, "rend_dist": allmap[6:7]}
+        if self.fused_post:
+            from gsr_b200.surfel_post import surfel_postprocess
+            out = {"render": image, **surfel_postprocess(allmap, self.view, self.proj, depth_ratio=0.0)}
+        else:
+            render_alpha = allmap[1:2]
+            render_normal = (allmap[2:5].permute(1, 2, 0) @ (self.view[:3, :3].T)).permute(2, 0, 1)
+            depth = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
+            surf_normal = self.depth_to_normal(depth).permute(2, 0, 1) * render_alpha.detach()
+            out = {"render": image, "normal": render_normal, "surf_normal": surf_normal, "rend_dist": allmap[6:7]}
         losses = self.loss_dict(out)
         losses["scaling_loss"] = self.lambda_scaling * scaling.prod(dim=1).mean()
         loss = sum(losses.values())
