@@ -107,21 +107,10 @@ sort_build_records(const uint32_t* __restrict__ offsets, uint64_t* __restrict__ 
     const uint32_t begin = offsets[tile], end = offsets[tile + 1];
     const int n = (int)(end - begin);
     if (n == 0) return;
-    uint64_t* gk = keys + begin;
-    int m = 1;
-    while (m < n) m <<= 1;
-    const uint64_t* sorted;
-    if (m <= SORT_SMEM_CAP) {
-        for (int i = threadIdx.x; i < m; i += blockDim.x) skeys[i] = i < n ? gk[i] : KEY_INF;
-        __syncthreads();
-        if (n > 1 && !(dbg & 1)) bitonic_sort<true>(skeys, n, m);
-        sorted = skeys;
-    } else {
-        bitonic_sort<false>(gk, n, m);
-        sorted = gk;
-    }
+    __shared__ BucketSortSmem bs;
+    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs);
+    (void)dbg;
     const float ox = (float)((tile % gx) * TILE), oy = (float)((tile / gx) * TILE);
-    if (dbg & 2) return;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t g = (uint32_t)(sorted[i] & 0xffffffffull);
         const float4* gp = reinterpret_cast<const float4*>(geom + g);

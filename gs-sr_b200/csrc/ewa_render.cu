@@ -37,7 +37,8 @@ ewa_build_records(const uint32_t* __restrict__ offsets, uint64_t* __restrict__ k
     const uint32_t begin = offsets[tile], end = offsets[tile + 1];
     const int n = (int)(end - begin);
     if (n == 0) return;
-    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys);
+    __shared__ BucketSortSmem bs;
+    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs);
     const float ox = (float)((tile % gx) * TILE), oy = (float)((tile / gx) * TILE);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t g = (uint32_t)(sorted[i] & 0xffffffffull);

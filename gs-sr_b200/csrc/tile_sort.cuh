@@ -42,9 +42,135 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* __restrict__ k, int n, in
     }
 }
 
+// ---- bucketed sort (n <= BUCKET_SORT_CAP) ------------------------------------------------------------------------
+// The keys of a tile are (depth bits, index): depth-dominated and spread over the view frustum.  Instead of a
+// 55-step bitonic network over the padded list, the keys are (1) partitioned in shared memory into B monotonic
+// depth buckets (block min / max of the depth bits, a linear map, a shared-memory histogram, one scan, one
+// scatter) and (2) every bucket (~8 keys) is put in order by ONE warp with rank counting: lane i holds key i and
+// counts the smaller keys of its bucket (keys are unique, so the ranks are a permutation).  Any bucket larger than
+// 32 * BUCKET_RANK_ROUNDS keys (degenerate depth distributions) sends the whole tile to the bitonic path.
+constexpr int BUCKET_SORT_CAP = SORT_SMEM_CAP / 2;    // two key arrays share the 32 KB of skeys[]
+constexpr int BUCKET_MAX = 256;
+constexpr int BUCKET_RANK_ROUNDS = 4;                 // a bucket may hold up to 128 keys
+
+struct BucketSortSmem {
+    uint32_t cnt[BUCKET_MAX];       // histogram, then exclusive offsets
+    uint32_t cur[BUCKET_MAX];       // scatter cursors
+    uint32_t dmin, dmax;
+    int overflow;
+};
+
+// keys in src[0..n) (shared), sorted result in dst[0..n) (shared).  Returns false (dst undefined, src intact) when a
+// bucket overflows.  All threads of the 256-thread CTA must call it.
+__device__ __forceinline__ bool bucket_sort_256(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, int n,
+                                                BucketSortSmem& sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // number of buckets: ~4 keys each, power of two in [8, BUCKET_MAX]
+    int B = 8;
+    while (B < BUCKET_MAX && B * 4 < n) B <<= 1;
+    if (threadIdx.x == 0) { sm.dmin = 0xffffffffu; sm.dmax = 0u; sm.overflow = 0; }
+    for (int i = threadIdx.x; i < BUCKET_MAX; i += blockDim.x) { sm.cnt[i] = 0u; }
+    __syncthreads();
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t d = (uint32_t)(src[i] >> 32);
+        lo = min(lo, d); hi = max(hi, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { atomicMin(&sm.dmin, lo); atomicMax(&sm.dmax, hi); }
+    __syncthreads();
+    const uint32_t dmin = sm.dmin;
+    // bucket = floor(offset * B / span) evaluated in float32: conversion and multiplication are monotonic, which is
+    // all the partition needs (the order inside a bucket comes from the exact 64-bit keys); clamped to B - 1
+    const float scale = (float)B / ((float)(sm.dmax - dmin) + 1.0f);
+    const int Bm1 = B - 1;
+    auto bucket_of = [&](uint64_t key) -> int {
+        const uint32_t off = (uint32_t)(key >> 32) - dmin;
+        return min((int)(__uint2float_rz(off) * scale), Bm1);
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&sm.cnt[bucket_of(src[i])], 1u);
+    __syncthreads();
+    if (warp == 0) {                                       // exclusive scan of <= 256 counters by one warp (8 per lane)
+        uint32_t v[BUCKET_MAX / 32], t = 0;
+#pragma unroll
+        for (int k = 0; k < BUCKET_MAX / 32; k++) { v[k] = sm.cnt[lane * (BUCKET_MAX / 32) + k]; t += v[k]; }
+        uint32_t x = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        uint32_t e = x - t;
+        bool over = false;
+#pragma unroll
+        for (int k = 0; k < BUCKET_MAX / 32; k++) {
+            over |= v[k] > 32u * BUCKET_RANK_ROUNDS;
+            sm.cnt[lane * (BUCKET_MAX / 32) + k] = e; sm.cur[lane * (BUCKET_MAX / 32) + k] = e; e += v[k];
+        }
+        if (__any_sync(0xffffffffu, over) && lane == 0) sm.overflow = 1;
+    }
+    __syncthreads();
+    if (sm.overflow) return false;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t k = src[i];
+        dst[atomicAdd(&sm.cur[bucket_of(k)], 1u)] = k;
+    }
+    __syncthreads();
+    // rank counting inside each bucket; one warp per bucket, in place (all reads of a bucket precede its writes)
+    for (int bkt = warp; bkt < B; bkt += blockDim.x / 32) {
+        const int first = (int)sm.cnt[bkt];
+        const int cntb = (int)sm.cur[bkt] - first;        // cursor ended at first + count
+        if (cntb <= 1) continue;
+        if (cntb <= 32) {                                   // the common case: one key per lane
+            const uint64_t mine = lane < cntb ? dst[first + lane] : KEY_INF;
+            int rank = 0;
+            for (int j = 0; j < cntb; j++) rank += dst[first + j] < mine;      // broadcast reads
+            __syncwarp();
+            if (lane < cntb) dst[first + rank] = mine;
+            continue;
+        }
+        uint64_t mine[BUCKET_RANK_ROUNDS];
+        int rank[BUCKET_RANK_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < BUCKET_RANK_ROUNDS; r++) {
+            const int i = lane + 32 * r;
+            mine[r] = i < cntb ? dst[first + i] : KEY_INF;
+            rank[r] = 0;
+        }
+        for (int j = 0; j < cntb; j++) {
+            const uint64_t other = dst[first + j];           // broadcast read
+#pragma unroll
+            for (int r = 0; r < BUCKET_RANK_ROUNDS; r++) rank[r] += other < mine[r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < BUCKET_RANK_ROUNDS; r++)
+            if (lane + 32 * r < cntb) dst[first + rank[r]] = mine[r];
+    }
+    __syncthreads();
+    return true;
+}
+
 // Sorts tile `tile`'s bucket (in shared memory when it fits, else in place in global memory) and
 // returns a pointer to the sorted keys; n = bucket size.  All threads of the CTA must call it.
-__device__ __forceinline__ const uint64_t* sort_tile_bucket(uint64_t* __restrict__ gk, int n, uint64_t* skeys) {
+// skeys: SORT_SMEM_CAP keys of shared memory; bs: scratch of the bucketed path.
+__device__ __forceinline__ const uint64_t* sort_tile_bucket(uint64_t* __restrict__ gk, int n, uint64_t* skeys,
+                                                            BucketSortSmem& bs) {
+    if (n > 32 && n <= BUCKET_SORT_CAP) {
+        uint64_t* a = skeys;
+        uint64_t* b = skeys + BUCKET_SORT_CAP;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = gk[i];
+        __syncthreads();
+        if (bucket_sort_256(a, b, n, bs)) return b;
+        // degenerate depth distribution: fall through to the bitonic network on the keys still in a[]
+        int m = 1;
+        while (m < n) m <<= 1;
+        for (int i = n + threadIdx.x; i < m; i += blockDim.x) a[i] = KEY_INF;
+        __syncthreads();
+        bitonic_sort<true>(a, n, m);
+        return a;
+    }
     int m = 1;
     while (m < n) m <<= 1;
     if (m <= SORT_SMEM_CAP) {
