@@ -108,8 +108,7 @@ sort_build_records(const uint32_t* __restrict__ offsets, uint64_t* __restrict__ 
     const int n = (int)(end - begin);
     if (n == 0) return;
     __shared__ BucketSortSmem bs;
-    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs);
-    (void)dbg;
+    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs, (dbg & 1) != 0);   // dbg bit 0: bitonic only
     const float ox = (float)((tile % gx) * TILE), oy = (float)((tile / gx) * TILE);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t g = (uint32_t)(sorted[i] & 0xffffffffull);

@@ -156,8 +156,8 @@ __device__ __forceinline__ bool bucket_sort_256(const uint64_t* __restrict__ src
 // returns a pointer to the sorted keys; n = bucket size.  All threads of the CTA must call it.
 // skeys: SORT_SMEM_CAP keys of shared memory; bs: scratch of the bucketed path.
 __device__ __forceinline__ const uint64_t* sort_tile_bucket(uint64_t* __restrict__ gk, int n, uint64_t* skeys,
-                                                            BucketSortSmem& bs) {
-    if (n > 32 && n <= BUCKET_SORT_CAP) {
+                                                            BucketSortSmem& bs, bool force_bitonic = false) {
+    if (n > 32 && n <= BUCKET_SORT_CAP && !force_bitonic) {
         uint64_t* a = skeys;
         uint64_t* b = skeys + BUCKET_SORT_CAP;
         for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = gk[i];
