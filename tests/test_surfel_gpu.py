@@ -102,6 +102,25 @@ def test_degenerate_depth_distributions_keep_the_reference_order(mode):
     assert_grads_close(out["grads"], orc["grads"], ["opacities", "colors", "means3D"])
 
 
+@pytest.mark.parametrize("M,deg", [(1, 0), (4, 1), (9, 2), (16, 1), (16, 3), (5, 1)])
+def test_sh_coefficient_counts_and_active_degrees(M, deg):
+    """SH kernels (sh.cu): coefficient rows of 3*M floats for every M the reference accepts (the staged fast path is
+    M = 16; other M take the generic staging), active degree below the stored one (early training), M not a square,
+    P not a multiple of 32; dL/dsh above the active degree must be exactly zero."""
+    P, W, H = 3001, 160, 96
+    sc = synth.make_scene(P, W, H, seed=50 + M + deg, sh=True, sigma_px=3.0, rotate_camera=True, bg=(0.2, 0.1, 0.3))
+    sc.shs = np.ascontiguousarray(sc.shs[:, :M, :])
+    sc.sh_degree = deg
+    gc, go = synth.make_upstream_grads(W, H, seed=60)
+    out = hz.run_product_surfel(sc, gc, go)
+    orc = hz.run_oracle_surfel(sc, gc, go)
+    assert_forward_close(out, orc)
+    assert_grads_close(out["grads"], orc["grads"], ["shs", "means3D", "opacities"])
+    n_active = min((deg + 1) ** 2, M)
+    assert np.all(out["grads"]["shs"][:, n_active:, :] == 0)
+    assert np.all(out["grads"]["shs"][out["radii"] == 0] == 0)
+
+
 def test_bucketed_tile_sort_gives_the_bitonic_order():
     """(depth bits, index) keys are unique, so any correct sort gives the same per-tile lists: the bucketed sort and the
     bitonic network must produce bit-identical images and gradients on a deep scene (lists of ~1000 entries)."""
