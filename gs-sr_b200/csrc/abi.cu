@@ -28,7 +28,8 @@ __global__ void scatter_keys(int, const float*, const float*, int, const CullRec
 __global__ void sort_build_records(const uint32_t*, uint64_t*, const GeomRec*, const float*, int, int, int, float4*,
                                    size_t, int);
 __global__ void surfel_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float*,
-                                  uint32_t*, float*, float*);
+                                  uint32_t*, float*, float*, float4*);
+template <bool USED>
 __global__ void surfel_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*,
                                   const float*, const uint32_t*, const float*, const float*, float*);
 int bwd_ctas_per_tile();
@@ -123,6 +124,7 @@ static ViewParams make_view(const float* view, const float* proj, const float* c
 
 // ---- runtime options (debug / measurement only; defaults are the product path) ----
 static int g_last_R = 0;      // num_rendered of the previous forward (sizing guess only)
+static int g_no_used_bits = 0;   // 1: never use the forward's "blended" bits (the path taken when P >= 2^23)
 static int g_dbg = 0;         // developer timing experiments (results invalid when non-zero)
 static int g_no_cull = -1;   // 1: contribution boxes disabled (every pair evaluated, as the reference does)
 static bool no_cull() {
@@ -177,6 +179,7 @@ int gsr_set_option(const char* name, int value) {
     if (!name) return GSR_E_INVALID;
     if (!strcmp(name, "no_cull")) { g_no_cull = value ? 1 : 0; return GSR_OK; }
     if (!strcmp(name, "dbg")) { g_dbg = value; return GSR_OK; }
+    if (!strcmp(name, "no_used_bits")) { g_no_used_bits = value ? 1 : 0; return GSR_OK; }
     set_error("gsr_set_option: unknown option %s", name);
     return GSR_E_INVALID;
 }
@@ -315,7 +318,8 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     }
     prof_begin(GSR_PROF_RENDER_FWD, s);
     surfel_render_fwd<<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
-                                                  iw.final_T, iw.n_contrib, out_color, out_others);
+                                                  iw.final_T, iw.n_contrib, out_color, out_others,
+                                                  (R > 0 && P < (1 << REC_USED_SHIFT) && !g_no_used_bits) ? bw.planes + 3 * bw.plane_stride : nullptr);
     prof_end(GSR_PROF_RENDER_FWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
     (void)N;
@@ -356,9 +360,12 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
     GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * GACC_STRIDE * sizeof(float), s));
     if (R > 0) {
         prof_begin(GSR_PROF_RENDER_BWD, s);
-        surfel_render_bwd<<<ntiles * bwd_ctas_per_tile(), 256 / bwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
-                                                      iw.final_T, iw.n_contrib, dL_dpix, dL_dothers,
-                                                      bw.gacc);
+        if (P < (1 << REC_USED_SHIFT) && !g_no_used_bits)
+            surfel_render_bwd<true><<<ntiles * bwd_ctas_per_tile(), 256 / bwd_ctas_per_tile(), 0, s>>>(
+                iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, dL_dpix, dL_dothers, bw.gacc);
+        else
+            surfel_render_bwd<false><<<ntiles * bwd_ctas_per_tile(), 256 / bwd_ctas_per_tile(), 0, s>>>(
+                iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, dL_dpix, dL_dothers, bw.gacc);
         prof_end(GSR_PROF_RENDER_BWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }

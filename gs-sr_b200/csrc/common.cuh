@@ -67,6 +67,12 @@ constexpr int CULL_EXACT = 0, CULL_ALWAYS = 1, CULL_NEVER = 2;
 //   plane 2 (QC): c.xyz, opacity       plane 5 (PC): colour.g, colour.b, sx', sy' (moment origin)
 constexpr int REC_PLANES = 6;
 constexpr uint32_t REC_FLAG_ALWAYS = 0x80000000u;   // conic is not an ellipse: evaluate on every pixel
+// When P < 2^23 the Gaussian index needs 23 bits and bits 23..30 of the same record word carry, per warp block of the
+// tile (8 blocks of 8x4 pixels), "the forward blended this entry on at least one pixel of the block" (set with
+// red.global.or by surfel_render_fwd, read back through the record stream by surfel_render_bwd, which then walks
+// exactly the contributing entries instead of repeating the cull test).
+constexpr int REC_USED_SHIFT = 23;
+constexpr uint32_t REC_INDEX_MASK_USED = (1u << REC_USED_SHIFT) - 1u;
 
 // Per-Gaussian gradient accumulator filled by the backward render (float atomics after the
 // in-warp reduction), consumed by the backward preprocess.  80 bytes:

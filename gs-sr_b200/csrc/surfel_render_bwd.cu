@@ -87,6 +87,8 @@ constexpr int BWD_WARPS = GSR_BWD_WARPS;      // warps per CTA: 8 = whole 16x16 
 constexpr int BWD_SPLIT = 8 / BWD_WARPS;      // CTAs per tile
 constexpr int BWD_MINB = BWD_WARPS == 8 ? 3 : (BWD_WARPS == 4 ? 6 : 12);
 
+// USED: the record word carries the forward's per-warp-block "blended" bits (P < 2^23), no cull test here
+template <bool USED>
 __global__ void __launch_bounds__(BWD_WARPS * 32, BWD_MINB)
 surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, const float* __restrict__ final_T,
@@ -181,8 +183,10 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 if (base + c0 >= wlast) continue;
                 const int e = c0 + lane;
                 bool hit = false;
-                if (e < cnt && base + e < wlast)
-                    hit = entry_hits_block(sb[0][e], sb[1][e], sb[2][e], sb[3][e], bx0, bx1, by0, by1);
+                if (e < cnt && base + e < wlast) {
+                    if (USED) hit = (__float_as_uint(sb[3][e].w) >> (REC_USED_SHIFT + warp)) & 1u;
+                    else hit = entry_hits_block(sb[0][e], sb[1][e], sb[2][e], sb[3][e], bx0, bx1, by0, by1);
+                }
                 uint32_t m = __ballot_sync(FULLMASK, hit);
                 while (m) {
                     const int bit = 31 - __clz(m);
@@ -260,7 +264,7 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                     const bool any_lowpass = __any_sync(FULLMASK, lowpass);
                     const float red = warp_reduce16_transposed(v, lane);
                     const float so = warp_sum(vo);
-                    const uint32_t g = __float_as_uint(qd.w) & ~REC_FLAG_ALWAYS;
+                    const uint32_t g = __float_as_uint(qd.w) & (USED ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS);
                     float* acc = gacc + (size_t)g * GACC_STRIDE;
                     const int vi = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
                     if ((lane & 1) == 0) atomicAdd(acc + vi, red);
@@ -288,6 +292,10 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     }
 }
 
+template __global__ void surfel_render_bwd<false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, const float*,
+                                                 const uint32_t*, const float*, const float*, float*);
+template __global__ void surfel_render_bwd<true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, const float*,
+                                                const uint32_t*, const float*, const float*, float*);
 int bwd_ctas_per_tile() { return BWD_SPLIT; }
 
 }  // namespace gsr

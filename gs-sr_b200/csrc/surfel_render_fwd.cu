@@ -33,11 +33,11 @@ namespace gsr {
 constexpr int FWD_WARPS = GSR_FWD_WARPS;      // warps per CTA: 8 = whole 16x16 tile, 4 = half tile (16x8)
 constexpr int FWD_SPLIT = 8 / FWD_WARPS;
 
-__global__ void __launch_bounds__(FWD_WARPS * 32)
+__global__ void __launch_bounds__(FWD_WARPS * 32, 32 / FWD_WARPS)
 surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, float* __restrict__ final_T,
                   uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
-                  float* __restrict__ out_others) {
+                  float* __restrict__ out_others, float4* __restrict__ mark_plane) {
     __shared__ __align__(128) float4 sbuf[2][REC_PLANES][RBATCH];
     __shared__ __align__(8) uint64_t full_bar[2];
 
@@ -57,6 +57,7 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     const int n = (int)(tile_offset[tile + 1] - range_x);
     const int nb = (n + RBATCH - 1) / RBATCH;
     const float4* src = planes + range_x;
+    const uint32_t idx_mask = mark_plane != nullptr ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS;
 
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
@@ -88,8 +89,10 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 bool hit = false;
                 if (e < cnt) hit = entry_hits_block(sb[0][e], sb[1][e], sb[2][e], sb[3][e], bx0, bx1, by0, by1);
                 uint32_t m = __ballot_sync(FULLMASK, hit);
+                uint32_t used = 0;                 // entries of this chunk blended on >= 1 pixel of this warp's block
                 while (m) {
-                    const int j = c0 + __ffs(m) - 1;
+                    const int bitpos = __ffs(m) - 1;
+                    const int j = c0 + bitpos;
                     m &= m - 1;
                     const float4 qa = sb[0][j], qb = sb[1][j], qc = sb[2][j], qd = sb[3][j];
                     PairEval ev = eval_pair(qa, qb, qc, qd, fx, fy);
@@ -97,6 +100,7 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                     if (__any_sync(FULLMASK, valid)) {
                         const float test_T = T * (1.0f - ev.alpha);
                         if (valid && test_T < T_EPS) { done = true; valid = false; }
+                        used |= 1u << bitpos;      // superset: also set when every contributing lane just terminated
                         if (valid) {
                             const float4 pn = sb[4][j], pc = sb[5][j];
                             const float w = ev.alpha * T;
@@ -109,7 +113,7 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                             const uint32_t pos = (uint32_t)(b * RBATCH + j + 1);
                             if (T > 0.5f) {
                                 med_depth = ev.depth;
-                                surf_idx = (int)(__float_as_uint(qd.w) & ~REC_FLAG_ALWAYS);
+                                surf_idx = (int)(__float_as_uint(qd.w) & idx_mask);
                                 mn0 = pn.x; mn1 = pn.y; mn2 = pn.z;
                                 med_contrib = pos;
                             }
@@ -121,6 +125,10 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                         if (__all_sync(FULLMASK, done)) { warp_done = true; break; }
                     }
                 }
+                // hand the contributing entries to the backward: one predicated red.or per chunk into the record word
+                if (mark_plane != nullptr && ((used >> lane) & 1u))
+                    atomicOr(reinterpret_cast<uint32_t*>(mark_plane + range_x + b * RBATCH + c0 + lane) + 3,
+                             1u << (REC_USED_SHIFT + warp));
             }
         }
         // stage is free once every warp is past it; refill it with batch b+2

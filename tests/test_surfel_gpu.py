@@ -121,6 +121,28 @@ def test_sh_coefficient_counts_and_active_degrees(M, deg):
     assert np.all(out["grads"]["shs"][out["radii"] == 0] == 0)
 
 
+def test_used_bits_path_equals_cull_path():
+    """P < 2^23: the forward marks, in the record word, which warp blocks blended each entry and the backward walks those
+    marks; P >= 2^23 (forced here with the no_used_bits option) repeats the cull test instead.  Both visit the same
+    contributing pairs in the same order, so images and gradients are bit-identical."""
+    import gsr_b200
+    sc = synth.make_scene(300000, 640, 400, seed=43)
+    gc, go = synth.make_upstream_grads(640, 400, seed=44)
+    tt = hz.to_torch(sc)
+    a = hz.run_product_surfel(sc, gc, go, tt=tt)
+    gsr_b200.lib().gsr_set_option(b"no_used_bits", 1)
+    try:
+        b = hz.run_product_surfel(sc, gc, go, tt=tt)
+    finally:
+        gsr_b200.lib().gsr_set_option(b"no_used_bits", 0)
+    assert np.array_equal(a["color"], b["color"]) and np.array_equal(a["others"], b["others"])
+    for k in a["grads"]:
+        if a["grads"][k] is not None:
+            x, y = a["grads"][k].astype(np.float64), b["grads"][k].astype(np.float64)
+            # the same pairs are summed; only the order of the float atomics into gacc differs between two launches
+            assert np.abs(x - y).max() <= 1e-5 * max(np.abs(y).max(), 1e-30), k
+
+
 def test_bucketed_tile_sort_gives_the_bitonic_order():
     """(depth bits, index) keys are unique, so any correct sort gives the same per-tile lists: the bucketed sort and the
     bitonic network must produce bit-identical images and gradients on a deep scene (lists of ~1000 entries)."""
