@@ -48,8 +48,8 @@ template <bool GEO>
 __global__ void ewa_build_records(const uint32_t*, uint64_t*, const EwaGeom*, const float*, const float*, int, float4*, size_t);
 template <bool GEO>
 __global__ void ewa_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float, float*,
-                               uint32_t*, float*, int*, float*, float*);
-template <int MODE>
+                               uint32_t*, float*, int*, float*, float*, float4*);
+template <int MODE, bool USED>
 __global__ void ewa_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
                                const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
 // ---- error string -------------------------------------------------------------
@@ -518,10 +518,12 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
         GSR_CUDA_CHECK(cudaGetLastError());
     }
     prof_begin(GSR_PROF_RENDER_FWD, s);
+    // plane 1 holds the idx|flag word that receives the forward's "blended" marks (P < 2^23)
+    float4* mark = (R > 0 && P < (1 << REC_USED_SHIFT) && !g_no_used_bits) ? bw.planes + 1 * bw.plane_stride : nullptr;
     if (a.geo) ewa_render_fwd<true><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
-                                                                iw.final_T, iw.n_contrib, a.out_color, a.out_observe, a.out_all_map, a.out_plane_depth);
+                                                                iw.final_T, iw.n_contrib, a.out_color, a.out_observe, a.out_all_map, a.out_plane_depth, mark);
     else ewa_render_fwd<false><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
-                                                           iw.final_T, iw.n_contrib, a.out_color, a.plane ? a.out_observe : nullptr, nullptr, nullptr);
+                                                           iw.final_T, iw.n_contrib, a.out_color, a.plane ? a.out_observe : nullptr, nullptr, nullptr, mark);
     prof_end(GSR_PROF_RENDER_FWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
     if (a.debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -572,16 +574,22 @@ static int ewa_backward(const EwaBwdArgs& a, const char* who) {
     GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * EWA_GACC * sizeof(float), s));
     if (R > 0) {
         prof_begin(GSR_PROF_RENDER_BWD, s);
-        if (a.geo)
-            ewa_render_bwd<2><<<ntiles * ewa_bwd_ctas_per_tile(), 256 / ewa_bwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
-                                                          iw.final_T, iw.n_contrib, a.all_map_pixels, a.dL_dpix, a.dL_dout_all_map,
-                                                          a.dL_dout_plane_depth, bw.gacc);
-        else if (a.plane)
-            ewa_render_bwd<1><<<ntiles * ewa_bwd_ctas_per_tile(), 256 / ewa_bwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
-                                                          iw.final_T, iw.n_contrib, nullptr, a.dL_dpix, nullptr, nullptr, bw.gacc);
-        else
-            ewa_render_bwd<0><<<ntiles * ewa_bwd_ctas_per_tile(), 256 / ewa_bwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
-                                                          iw.final_T, iw.n_contrib, nullptr, a.dL_dpix, nullptr, nullptr, bw.gacc);
+        const bool used = P < (1 << REC_USED_SHIFT) && !g_no_used_bits;
+        const dim3 bgrid(ntiles * ewa_bwd_ctas_per_tile()), bblock(256 / ewa_bwd_ctas_per_tile());
+#define GSR_EWA_BWD(MODE, USED, AMP, DAM, DPD)                                                                               \
+    ewa_render_bwd<MODE, USED><<<bgrid, bblock, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, \
+                                                        focal_x, focal_y, iw.final_T, iw.n_contrib, AMP, a.dL_dpix, DAM, DPD, bw.gacc)
+        if (a.geo) {
+            if (used) GSR_EWA_BWD(2, true, a.all_map_pixels, a.dL_dout_all_map, a.dL_dout_plane_depth);
+            else GSR_EWA_BWD(2, false, a.all_map_pixels, a.dL_dout_all_map, a.dL_dout_plane_depth);
+        } else if (a.plane) {
+            if (used) GSR_EWA_BWD(1, true, nullptr, nullptr, nullptr);
+            else GSR_EWA_BWD(1, false, nullptr, nullptr, nullptr);
+        } else {
+            if (used) GSR_EWA_BWD(0, true, nullptr, nullptr, nullptr);
+            else GSR_EWA_BWD(0, false, nullptr, nullptr, nullptr);
+        }
+#undef GSR_EWA_BWD
         prof_end(GSR_PROF_RENDER_BWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }

@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(TILE_PIX)
 ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W, int H,
                int gx, const float* __restrict__ bg, float focal_x, float focal_y, float* __restrict__ final_T,
                uint32_t* __restrict__ n_contrib, float* __restrict__ out_color, int* __restrict__ out_observe,
-               float* __restrict__ out_all_map, float* __restrict__ out_plane_depth) {
+               float* __restrict__ out_all_map, float* __restrict__ out_plane_depth, float4* __restrict__ mark_plane) {
+    // mark_plane != NULL (P < 2^23): bits 23..30 of the record's idx|flag word get "blended by warp block w" marks
+    // for the backward (see common.cuh REC_USED_SHIFT and surfel_render_fwd.cu)
     constexpr int NPL = GEO ? EWA_PLANES_GEO : EWA_PLANES;
     __shared__ __align__(128) float4 sbuf[2][NPL][RBATCH];
     __shared__ __align__(8) uint64_t full_bar[2];
@@ -120,6 +122,7 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
     const int n = (int)(tile_offset[tile + 1] - range_x);
     const int nb = (n + RBATCH - 1) / RBATCH;
     const float4* src = planes + range_x;
+    const uint32_t idx_mask = mark_plane != nullptr ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS;
 
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
@@ -149,8 +152,10 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                 bool hit = false;
                 if (e < cnt) hit = ewa_entry_hits_block(sb[0][e], sb[1][e], bx0, bx1, by0, by1);
                 uint32_t m = __ballot_sync(FULLMASK, hit);
+                uint32_t used = 0;
                 while (m) {
-                    const int j = c0 + __ffs(m) - 1;
+                    const int bitpos = __ffs(m) - 1;
+                    const int j = c0 + bitpos;
                     m &= m - 1;
                     const float4 p0 = sb[0][j], p1 = sb[1][j];
                     const EwaEval ev = ewa_eval(p0, p1, fx, fy);
@@ -158,6 +163,7 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                     if (__any_sync(FULLMASK, valid)) {
                         const float test_T = T * (1.0f - ev.alpha);
                         if (valid && test_T < T_EPS) { done = true; valid = false; }
+                        used |= 1u << bitpos;
                         if (valid) {
                             const float4 pc = sb[2][j];
                             const float w = ev.alpha * T;
@@ -170,7 +176,7 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                         if (out_observe != nullptr) {   // L/forward.cu:381-384, T before the update
                             const uint32_t ob = __ballot_sync(FULLMASK, valid && T > 0.5f);
                             if (ob != 0u && lane == 0)
-                                atomicAdd(out_observe + (__float_as_uint(p1.w) & ~REC_FLAG_ALWAYS), __popc(ob));
+                                atomicAdd(out_observe + (__float_as_uint(p1.w) & idx_mask), __popc(ob));
                         }
                         if (valid) {
                             T = test_T;
@@ -179,6 +185,9 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                         if (__all_sync(FULLMASK, done)) { warp_done = true; break; }
                     }
                 }
+                if (mark_plane != nullptr && ((used >> lane) & 1u))
+                    atomicOr(reinterpret_cast<uint32_t*>(mark_plane + range_x + b * RBATCH + c0 + lane) + 3,
+                             1u << (REC_USED_SHIFT + warp));
             }
         }
         const int all_done = __syncthreads_and(warp_done);
@@ -210,9 +219,9 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
     }
 }
 template __global__ void ewa_render_fwd<false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-                                               float*, uint32_t*, float*, int*, float*, float*);
+                                               float*, uint32_t*, float*, int*, float*, float*, float4*);
 template __global__ void ewa_render_fwd<true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-                                              float*, uint32_t*, float*, int*, float*, float*);
+                                              float*, uint32_t*, float*, int*, float*, float*, float4*);
 
 // ---- backward -----------------------------------------------------------------------------------
 // Transposed warp reduction of 16 per-lane values (see surfel_render_bwd.cu): afterwards lane L holds
@@ -261,7 +270,8 @@ __device__ __forceinline__ float ewa_reduce16(float (&v)[16], int lane) {
 constexpr int EWA_BWD_WARPS = 4, EWA_BWD_SPLIT = 8 / EWA_BWD_WARPS, EWA_BWD_STAGES = 3;
 int ewa_bwd_ctas_per_tile() { return EWA_BWD_SPLIT; }
 
-template <int MODE>
+// USED: walk the forward's "blended" marks in the record word instead of repeating the cull test (P < 2^23)
+template <int MODE, bool USED>
 __global__ void __launch_bounds__(EWA_BWD_WARPS * 32, 6)
 ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W, int H,
                int gx, const float* __restrict__ bg, float focal_x, float focal_y, const float* __restrict__ final_T,
@@ -355,7 +365,10 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                 if (base + c0 >= wlast) continue;
                 const int e = c0 + lane;
                 bool hit = false;
-                if (e < cnt && base + e < wlast) hit = ewa_entry_hits_block(sb[0][e], sb[1][e], bx0, bx1, by0, by1);
+                if (e < cnt && base + e < wlast) {
+                    if (USED) hit = (__float_as_uint(sb[1][e].w) >> (REC_USED_SHIFT + warp)) & 1u;
+                    else hit = ewa_entry_hits_block(sb[0][e], sb[1][e], bx0, bx1, by0, by1);
+                }
                 uint32_t m = __ballot_sync(FULLMASK, hit);
                 while (m) {
                     const int bit = 31 - __clz(m);
@@ -409,7 +422,7 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                         if (MODE != 0) { v[9] = fabsf(v[0]); v[10] = fabsf(v[1]); }
                     }
                     const float red = ewa_reduce16(v, lane);
-                    const uint32_t g = __float_as_uint(p1.w) & ~REC_FLAG_ALWAYS;
+                    const uint32_t g = __float_as_uint(p1.w) & (USED ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS);
                     const int vi = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
                     if ((lane & 1) == 0 && vi < NV) atomicAdd(gacc + (size_t)g * EWA_GACC + vi, red);
                 }
@@ -429,11 +442,17 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
         if (++stage == EWA_BWD_STAGES) { stage = 0; parity ^= 1u; }
     }
 }
-template __global__ void ewa_render_bwd<0>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-                                           const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
-template __global__ void ewa_render_bwd<1>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-                                           const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
-template __global__ void ewa_render_bwd<2>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-                                           const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+template __global__ void ewa_render_bwd<0, false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
+    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+template __global__ void ewa_render_bwd<0, true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
+    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+template __global__ void ewa_render_bwd<1, false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
+    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+template __global__ void ewa_render_bwd<1, true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
+    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+template __global__ void ewa_render_bwd<2, false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
+    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+template __global__ void ewa_render_bwd<2, true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
+    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
 
 }  // namespace gsr

@@ -61,6 +61,32 @@ def test_ewa_product_matches_reference_cuda_build(plane):
     check_ewa_grads(out["grads"], ref["grads"], ewa_grad_keys(sc, kw))
 
 
+@pytest.mark.parametrize("plane", [False, True])
+def test_ewa_used_bits_path_equals_cull_path(plane):
+    """Same contract as the surfel test: the backward that walks the forward's marks (P < 2^23) and the one that repeats
+    the cull test (forced with no_used_bits) visit the same pairs."""
+    import gsr_b200
+    sc = synth.make_scene(200000, 640, 400, seed=45, scale_dims=3)
+    gc, go = synth.make_upstream_grads(640, 400, seed=46, n_others=6, zero_from=6)
+    kw = dict(g_color=gc, plane=plane)
+    if plane:
+        kw.update(all_map=synth.make_all_map(sc), g_all_map=np.ascontiguousarray(go[:5]), g_plane_depth=np.ascontiguousarray(go[5:6]))
+    tt = hz.to_torch(sc)
+    a = hz.run_product_gauss(sc, tt=tt, **kw)
+    gsr_b200.lib().gsr_set_option(b"no_used_bits", 1)
+    try:
+        b = hz.run_product_gauss(sc, tt=tt, **kw)
+    finally:
+        gsr_b200.lib().gsr_set_option(b"no_used_bits", 0)
+    assert np.array_equal(a["color"], b["color"]) and np.array_equal(a["radii"], b["radii"])
+    if plane:
+        assert np.array_equal(a["observe"], b["observe"]) and np.array_equal(a["out_all_map"], b["out_all_map"])
+    for k in a["grads"]:
+        if a["grads"][k] is not None and b["grads"][k] is not None and a["grads"][k].size:
+            x, y = a["grads"][k].astype(np.float64), b["grads"][k].astype(np.float64)
+            assert np.abs(x - y).max() <= 1e-5 * max(np.abs(y).max(), 1e-30), k
+
+
 def test_ewa_culling_never_changes_results():
     """no_cull evaluates every (pixel, splat) pair of the reference's tile lists; the culled path must give
     bit-identical images and last contributors (identical blend order)."""
