@@ -80,9 +80,10 @@ size_t ImageWs::carve(ImageWs& w, char* base, int W, int H, int nT, int nC) {
     size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
     w.final_T = c.take<float>(nT * N);
     w.n_contrib = c.take<uint32_t>(nC * N);
-    w.tile_count = c.take<uint32_t>(tiles + 2);
+    w.tile_count = c.take<uint32_t>(tiles * TILE_CTR_STRIDE);
     w.tile_offset = c.take<uint32_t>(tiles + 1);
-    w.tile_cursor = c.take<uint32_t>(tiles);
+    w.tile_cursor = c.take<uint32_t>(tiles * TILE_CTR_STRIDE);
+    w.total = c.take<uint32_t>(8);
     return c.used + 256;
 }
 size_t BinWs::carve(BinWs& w, char* base, int64_t R, int P, int nplanes, int gacc_stride) {
@@ -236,7 +237,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     if (!ibase) { set_error("imageBuffer callback failed (%zu bytes)", ibytes); return GSR_E_ALLOC; }
     ImageWs::carve(iw, align256(ibase), W, H);
     // tile_count, tile_offset and tile_cursor are adjacent: one memset clears all three
-    GSR_CUDA_CHECK(cudaMemsetAsync(iw.tile_count, 0, (size_t)((char*)(iw.tile_cursor + ntiles) - (char*)iw.tile_count), s));
+    GSR_CUDA_CHECK(cudaMemsetAsync(iw.tile_count, 0, (size_t)((char*)(iw.total + 8) - (char*)iw.tile_count), s));
     ht.mark("imgbuf");
 
     int R = 0;
@@ -262,7 +263,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         prof_begin(GSR_PROF_SCAN, s);
-        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.tile_count + ntiles,
+        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total,
                                      gw.flags);
         prof_end(GSR_PROF_SCAN, s);
         GSR_CUDA_CHECK(cudaGetLastError());
@@ -282,7 +283,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         // num_rendered sizes the binning buffer: the same single read-back as the reference
         // (S/rasterizer_impl.cu:282); the prefiltered flag rides along.
         uint32_t rb[2] = {0u, 0u};
-        GSR_CUDA_CHECK(cudaMemcpyAsync(rb, iw.tile_count + ntiles, 8, cudaMemcpyDeviceToHost, s));
+        GSR_CUDA_CHECK(cudaMemcpyAsync(rb, iw.total, 8, cudaMemcpyDeviceToHost, s));
         GSR_CUDA_CHECK(cudaStreamSynchronize(s));
         if (rb[1]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
         if (rb[0] > 0x7fffff00u) { set_error("num_rendered overflow (%u)", rb[0]); return GSR_E_OVERFLOW; }
@@ -446,7 +447,7 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
     char* ibase = a.imageBuffer(a.user, ibytes);
     if (!ibase) { set_error("imageBuffer callback failed (%zu bytes)", ibytes); return GSR_E_ALLOC; }
     ImageWs::carve(iw, align256(ibase), W, H, 1, 1);
-    GSR_CUDA_CHECK(cudaMemsetAsync(iw.tile_count, 0, (size_t)((char*)(iw.tile_cursor + ntiles) - (char*)iw.tile_count), s));
+    GSR_CUDA_CHECK(cudaMemsetAsync(iw.tile_count, 0, (size_t)((char*)(iw.total + 8) - (char*)iw.tile_count), s));
     if (a.plane && P > 0) GSR_CUDA_CHECK(cudaMemsetAsync(a.out_observe, 0, (size_t)P * sizeof(int), s));
     if (a.plane && !a.geo) {   // torch::full(..., 0) in the reference glue (L/rasterize_points.cu:75-76)
         if (a.out_all_map) GSR_CUDA_CHECK(cudaMemsetAsync(a.out_all_map, 0, NUM_ALL_MAP * N * sizeof(float), s));
@@ -473,7 +474,7 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
         prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         prof_begin(GSR_PROF_SCAN, s);
-        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.tile_count + ntiles, gw.flags);
+        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total, gw.flags);
         prof_end(GSR_PROF_SCAN, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         // speculative binning buffer before the read-back (see gsr_surfel_forward)
@@ -486,7 +487,7 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
             if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bcap); return GSR_E_ALLOC; }
         }
         uint32_t rb[2] = {0u, 0u};
-        GSR_CUDA_CHECK(cudaMemcpyAsync(rb, iw.tile_count + ntiles, 8, cudaMemcpyDeviceToHost, s));
+        GSR_CUDA_CHECK(cudaMemcpyAsync(rb, iw.total, 8, cudaMemcpyDeviceToHost, s));
         GSR_CUDA_CHECK(cudaStreamSynchronize(s));
         if (rb[1]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
         if (rb[0] > 0x7fffff00u) { set_error("num_rendered overflow (%u)", rb[0]); return GSR_E_OVERFLOW; }

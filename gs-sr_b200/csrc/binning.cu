@@ -32,7 +32,7 @@ tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict_
     __syncthreads();
     for (int base = 0; base < ntiles; base += 1024) {
         const int i = base + threadIdx.x;
-        const uint32_t v = i < ntiles ? counts[i] : 0u;
+        const uint32_t v = i < ntiles ? counts[(size_t)i * TILE_CTR_STRIDE] : 0u;
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -52,7 +52,7 @@ tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict_
         }
         __syncthreads();
         const uint32_t excl = carry + warp_sums[warp] + (x - v);
-        if (i < ntiles) { offsets[i] = excl; cursors[i] = excl; }
+        if (i < ntiles) { offsets[i] = excl; cursors[(size_t)i * TILE_CTR_STRIDE] = excl; }
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
@@ -69,30 +69,42 @@ scatter_keys(int P, const float* __restrict__ centre_x, const float* __restrict_
              uint32_t* __restrict__ cursors, uint64_t* __restrict__ keys) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
-    const int r = radii[idx];
-    if (r <= 0) return;
-    const uint32_t mask = masks[idx];
-    if (mask == 0u) return;
-    // screen centre the rect was built from: a strided view into the variant's per-Gaussian record
-    const float cx = centre_x[(size_t)idx * centre_stride], cy = centre_y[(size_t)idx * centre_stride];
-    const uint64_t key = ((uint64_t)__float_as_uint(depths[idx]) << 32) | (uint32_t)idx;
+    // all five per-Gaussian loads are issued together (one memory round trip; values of culled Gaussians are in
+    // bounds and ignored), then the gates
+    const int r = __ldg(radii + idx);
+    const uint32_t mask = __ldg(masks + idx);
+    const float cx = __ldg(centre_x + (size_t)idx * centre_stride), cy = __ldg(centre_y + (size_t)idx * centre_stride);
+    const uint32_t dbits = __float_as_uint(__ldg(depths + idx));
+    if (r <= 0 || mask == 0u) return;
+    const uint64_t key = ((uint64_t)dbits << 32) | (uint32_t)idx;
     int x0, y0, x1, y1;
     get_rect(cx, cy, r, gx, gy, x0, y0, x1, y1);
     if (mask != MASK_RETEST) {
-        // the preprocess recorded which tiles of the (<= 32 tile) rect passed the test
+        // the preprocess recorded which tiles of the (<= 32 tile) rect passed the test; up to four returning
+        // atomics are in flight per round (the kernel is bound by memory round trips, not by issue)
         const int w = x1 - x0;
         uint32_t m = mask;
         while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            const int tile = (y0 + k / w) * gx + (x0 + k % w);
-            keys[atomicAdd(&cursors[tile], 1u)] = key;
+            uint32_t pos[4];
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    pos[u] = atomicAdd(&cursors[(size_t)((y0 + k / w) * gx + (x0 + k % w)) * TILE_CTR_STRIDE], 1u);
+                    cnt = u + 1;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (u < cnt) keys[pos[u]] = key;
         }
     } else {
         const CullRec cr = cull[idx];
         for (int y = y0; y < y1; y++)
             for (int x = x0; x < x1; x++)
-                if (tile_may_contribute(cr, cx, cy, x, y)) keys[atomicAdd(&cursors[y * gx + x], 1u)] = key;
+                if (tile_may_contribute(cr, cx, cy, x, y)) keys[atomicAdd(&cursors[(size_t)(y * gx + x) * TILE_CTR_STRIDE], 1u)] = key;
     }
 }
 

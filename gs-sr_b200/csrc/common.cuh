@@ -94,6 +94,10 @@ struct Carver {
     }
 };
 
+// Per-tile atomic counters (count pass of the preprocess, cursors of the scatter) are spaced one 128-byte line apart:
+// the L2 atomic unit serialises per line, and 32 neighbouring tiles sharing a line made the two passes wait on
+// ~30 k queued atomics per line (scatter_keys: 88 % long-scoreboard stalls, 12 % issue).
+constexpr int TILE_CTR_STRIDE = 32;
 constexpr uint32_t MASK_RETEST = 0xffffffffu;   // rect larger than 32 tiles: scatter re-runs the tile test
 
 struct GeomWs {      // geometryBuffer
@@ -110,9 +114,10 @@ struct GeomWs {      // geometryBuffer
 struct ImageWs {     // imageBuffer
     float* final_T;      // 3N: T, M1, M2   (S/cuda_rasterizer/forward.cu:429-437)
     uint32_t* n_contrib; // 2N: last contributor, median contributor
-    uint32_t* tile_count;   // tiles (+1: [tiles] = total R written by tile_scan)
+    uint32_t* tile_count;   // tiles x TILE_CTR_STRIDE: counter of tile t at [t * TILE_CTR_STRIDE]
     uint32_t* tile_offset;  // tiles + 1: tile t owns list entries [offset[t], offset[t+1])
-    uint32_t* tile_cursor;  // tiles: scatter cursors
+    uint32_t* tile_cursor;  // tiles x TILE_CTR_STRIDE: scatter cursors, same spacing
+    uint32_t* total;        // [0] = R, [1] = prefiltered-violation flag (written by tile_scan, read back by the host)
     // nT / nC: per-pixel float / uint32 planes (surfel 3 + 2, EWA 1 + 1)
     static size_t carve(ImageWs& w, char* base, int W, int H, int nT = 3, int nC = 2);
 };

@@ -149,7 +149,7 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
         for (int ty = y0; ty < y1; ty++)
             for (int tx = x0; tx < x1; tx++, k++)
                 if (tile_may_contribute(cr, cx, cy, tx, ty)) {
-                    atomicAdd(&tile_count[ty * vc.gx + tx], 1u);
+                    atomicAdd(&tile_count[(size_t)(ty * vc.gx + tx) * TILE_CTR_STRIDE], 1u);
                     if (k < 32) m |= 1u << k;
                 }
         mask_out = area <= 32 ? m : MASK_RETEST;
