@@ -155,3 +155,22 @@ def test_tsdf_fuse_argument_validation_without_gpu():
     assert L.gsr_tsdf_fuse(4, None, 0, None, 1.0, 0.01, 0, None, 1, None, None, None, None) == -1   # samples required
     assert L.gsr_tsdf_fuse(0, None, 0, None, 1.0, 0.01, 0, None, 1, None, None, None, None) == 0    # nothing to do
     assert b"gsr_tsdf_fuse" in L.gsr_last_error()
+
+
+def test_header_is_plain_c99():
+    """The drop-in boundary is a C ABI: include/gsr_b200.h must compile as C (no C++, no torch / CUDA types) and a C
+    program that links only against the shared library must resolve every declared symbol."""
+    import subprocess
+    import tempfile
+    import gsr_b200
+    src = '#include "gsr_b200.h"\n#include <stdio.h>\nint main(void) {\n  printf("%d %s\\n", gsr_abi_version(), gsr_build_arch());\n'
+    src += "  typedef void (*fn)(void);\n  fn p[] = {" + ", ".join(f"(fn){n}" for n in declared_functions()) + "};\n  return p[0] == 0;\n}\n"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        libdir = os.path.dirname(gsr_b200.LIB_PATH)
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", INCLUDE, c, "-o", exe, "-L", libdir,
+                        "-l:libgsr_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["1", "sm_100a"]
