@@ -87,6 +87,40 @@ def test_ewa_used_bits_path_equals_cull_path(plane):
             assert np.abs(x - y).max() <= 1e-5 * max(np.abs(y).max(), 1e-30), k
 
 
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_ewa_random_configuration_sweep(seed):
+    """Seeded sweep (3DGS for even seeds, plane + render_geo for odd): image shapes, splat sizes, opacity ranges, points
+    behind the camera; radii / out_observe equal the reference build, colour matches the oracle."""
+    from oracle import refcuda
+    rng = np.random.default_rng(5000 + seed)
+    plane = bool(seed & 1)
+    W = int(rng.choice([16, 23, 64, 97, 130, 256])); H = int(rng.choice([16, 31, 48, 75, 128]))
+    P = int(rng.choice([1, 7, 200, 1500, 4000]))
+    sc = synth.make_scene(P, W, H, seed=6000 + seed, scale_dims=3, sigma_px=float(rng.choice([0.3, 1.0, 3.0, 9.0, 25.0])),
+                          opacity_sigma=float(rng.choice([0.5, 1.5, 4.0])), rotate_camera=bool(rng.integers(0, 2)),
+                          behind_fraction=float(rng.choice([0.0, 0.3])), bg=tuple(rng.uniform(0, 1, 3)))
+    gc, go = synth.make_upstream_grads(W, H, seed=7000 + seed, n_others=6, zero_from=6)
+    kw = dict(g_color=gc, plane=plane)
+    if plane:
+        kw.update(all_map=synth.make_all_map(sc), g_all_map=np.ascontiguousarray(go[:5]), g_plane_depth=np.ascontiguousarray(go[5:6]))
+    out = hz.run_product_gauss(sc, **kw)
+    orc = hz.run_oracle_gauss(sc, **kw)
+    assert hz.rel_linf(out["color"], orc["color"], 2e-3) <= 1e-4
+    assert ((out["radii"] > 0) != (orc["radii"] > 0)).sum() <= max(1, P // 500)
+    for k in ("opacities", "means3D", "colors"):
+        assert np.isfinite(out["grads"][k]).all()
+    if refcuda.available("plane" if plane else "gaussian"):
+        ref = hz.run_refcuda_gauss(sc, **kw)
+        assert (out["radii"] != ref["radii"]).sum() <= max(1, P // 2000)
+        if plane:
+            assert (out["observe"] != ref["observe"]).sum() <= max(1, P // 500)
+        if (ref["radii"] > 0).sum() >= 50:
+            g = {k: v for k, v in ref["grads"].items() if k in ("opacities", "means3D", "colors", "scales")}
+            res = hz.compare_grads_keys(out["grads"], g, list(g.keys()), verbose=False, outlier_frac=2e-3)
+            for k, (linf, l2) in res.items():
+                assert linf <= 1e-3 and l2 <= 1e-3, (k, linf, l2)
+
+
 def test_ewa_culling_never_changes_results():
     """no_cull evaluates every (pixel, splat) pair of the reference's tile lists; the culled path must give
     bit-identical images and last contributors (identical blend order)."""
