@@ -1,12 +1,16 @@
 """Developer helper (not a pytest): A/B kernel variants selected by gsr_set_option("dbg", v) on cfg-B:
-library cudaEvent times per kernel + gradient agreement with the default variant."""
+library cudaEvent times per kernel + gradient agreement with the default variant.  dbg bit 0 = per-tile bitonic
+network instead of the bucketed sort; other library builds can be compared with GSR_B200_LIB=/path/to/lib.so.
+
+    python tests/gpu_variants.py 0 1
+"""
 import ctypes, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import gpu_profile as gp
 import torch, gsr_b200
 P, W, H = 2_000_000, 1600, 1060
-variants = [int(v) for v in sys.argv[1:]] or [0]
+variants = [int(v) for v in sys.argv[1:]] or [0, 1]
 sc, tt, gct, got, rast, leaves, m2d = gp.setup(P, W, H)
 L = gsr_b200.lib()
 
