@@ -27,6 +27,7 @@ __global__ void scatter_keys(int, const float*, const float*, int, const CullRec
                              const uint32_t*, int, int, uint32_t*, uint64_t*);
 __global__ void sort_build_records(const uint32_t*, uint64_t*, const GeomRec*, const float*, int, int, int, float4*,
                                    size_t, int);
+template <bool MARK>
 __global__ void surfel_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float*,
                                   uint32_t*, float*, float*, float4*);
 template <bool USED>
@@ -318,9 +319,14 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         GSR_CUDA_CHECK(cudaGetLastError());
     }
     prof_begin(GSR_PROF_RENDER_FWD, s);
-    surfel_render_fwd<<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background,
-                                                  iw.final_T, iw.n_contrib, out_color, out_others,
-                                                  (R > 0 && P < (1 << REC_USED_SHIFT) && !g_no_used_bits) ? bw.planes + 3 * bw.plane_stride : nullptr);
+    if (R > 0 && P < (1 << REC_USED_SHIFT) && !g_no_used_bits)
+        surfel_render_fwd<true><<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(
+            iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, out_color, out_others,
+            bw.planes + 3 * bw.plane_stride);
+    else
+        surfel_render_fwd<false><<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(
+            iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, out_color, out_others,
+            nullptr);
     prof_end(GSR_PROF_RENDER_FWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
     (void)N;

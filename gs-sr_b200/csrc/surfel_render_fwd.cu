@@ -33,6 +33,8 @@ namespace gsr {
 constexpr int FWD_WARPS = GSR_FWD_WARPS;      // warps per CTA: 8 = whole 16x16 tile, 4 = half tile (16x8)
 constexpr int FWD_SPLIT = 8 / FWD_WARPS;
 
+// MARK: P < 2^23, the record word has room for the per-warp-block "blended" marks handed to the backward
+template <bool MARK>
 __global__ void __launch_bounds__(FWD_WARPS * 32, 32 / FWD_WARPS)
 surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, float* __restrict__ final_T,
@@ -57,7 +59,7 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     const int n = (int)(tile_offset[tile + 1] - range_x);
     const int nb = (n + RBATCH - 1) / RBATCH;
     const float4* src = planes + range_x;
-    const uint32_t idx_mask = mark_plane != nullptr ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS;
+    constexpr uint32_t idx_mask = MARK ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS;
 
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
@@ -126,7 +128,7 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                     }
                 }
                 // hand the contributing entries to the backward: one predicated red.or per chunk into the record word
-                if (mark_plane != nullptr && ((used >> lane) & 1u))
+                if (MARK && ((used >> lane) & 1u))
                     atomicOr(reinterpret_cast<uint32_t*>(mark_plane + range_x + b * RBATCH + c0 + lane) + 3,
                              1u << (REC_USED_SHIFT + warp));
             }
@@ -170,6 +172,10 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     }
 }
 
+template __global__ void surfel_render_fwd<false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float*, uint32_t*,
+                                                 float*, float*, float4*);
+template __global__ void surfel_render_fwd<true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float*, uint32_t*,
+                                                float*, float*, float4*);
 int fwd_ctas_per_tile() { return FWD_SPLIT; }
 
 }  // namespace gsr
