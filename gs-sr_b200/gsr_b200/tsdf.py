@@ -10,7 +10,7 @@ Same argument names and meaning as the reference's nested ``compute_unbounded_ts
 difference is that ``inv_contraction`` is a flag (anything but None selects the reference's
 ``unnormalize(uncontract(x))`` with this object's center / radius, :187-193, :248-250) because the
 contraction runs inside the CUDA kernel.  Views are fused many per kernel launch (``gsr_tsdf_fuse``,
-gs-sr_b200/csrc/tsdf.cu; 16 depth-only / 8 depth+RGB 1600x1060 views per launch); no CPU / PyTorch fallback.
+gs-sr_b200/csrc/tsdf.cu; 17 depth-only / 8 depth+RGB 1600x1060 views per launch); no CPU / PyTorch fallback.
 """
 from __future__ import annotations
 
