@@ -15,6 +15,12 @@ One JSON line on rank 0:
   value  : whole-job Gaussians/s, inputs resident in HBM (CUDA events, max over ranks)
   e2e    : same metric with the step's inputs copied from pinned host memory and the rendered
            colour image copied back inside the timed region
+  step_ms: median / p10 / p90 of the K per-step event times (BASELINE.md's reporting protocol)
+  evals  : K_eval (per tile 256 x list entries walked before the block exits, reference definition,
+           counted by the CPU port on the full frame) and FP32 pair evaluations/s = K_eval / step time
+  extras : the other hot-path workloads (cfg-A surfel, 3DGS 1M, plane cfg-4, visible_filter 2M, distCUDA2 1M), same
+           timing for both arms (tests/bench_extras.py)
+  train  : BASELINE's "train iters/s" on config 2, with the fused image-space ops and rasterizer-only
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
 --impl reference times the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libref_surfel.so,
 compiled from /root/reference by oracle/build_ref.sh) on the same workload; when that library
@@ -228,14 +234,15 @@ def run_ours(args, rank, world, device):
     for _ in range(args.warmup):
         step(dev)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    e0.record()
-    for _ in range(args.steps):
+    ev[0].record()
+    for i in range(args.steps):
         step(dev)
-    e1.record()
+        ev[i + 1].record()
     barrier()
-    ms_resident = shard.max_over_ranks(e0.elapsed_time(e1), device)
+    ms_resident = shard.max_over_ranks(ev[0].elapsed_time(ev[-1]), device)
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
 
     # end-to-end: H2D of the step's inputs from pinned memory + D2H of the rendered image
     out_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
@@ -260,7 +267,7 @@ def run_ours(args, rank, world, device):
     kernel_ms = {n: float(acc[i] / nprof) for i, n in enumerate(PROF_NAMES)}
     V = int((state["radii"] > 0).sum().item())
     return dict(ms_resident=ms_resident, ms_e2e=ms_e2e, clocks=clocks, h2d=h2d, d2h=d2h, kernel_ms=kernel_ms, V=V,
-                sc=sc, checksum=float(state["color"].double().sum().item()))
+                sc=sc, checksum=float(state["color"].double().sum().item()), step_ms=step_ms)
 
 
 def run_reference_cuda(args, rank, world, device):
@@ -288,24 +295,31 @@ def run_reference_cuda(args, rank, world, device):
     for _ in range(args.warmup):
         step(dev)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
         step(dev)
-    e1.record()
+        ev[i + 1].record()
     barrier()
-    ms_resident = shard.max_over_ranks(e0.elapsed_time(e1), device)
+    ms_resident = shard.max_over_ranks(ev[0].elapsed_time(ev[-1]), device)
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     out_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
     pipelined_e2e(step, host, dev, out_host, 2, barrier)
     ms_e2e = shard.max_over_ranks(pipelined_e2e(step, host, dev, out_host, args.steps, barrier), device)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     return dict(ms_resident=ms_resident, ms_e2e=ms_e2e, h2d=h2d, d2h=out_host.numel() * 4, R=int(state["R"]),
-                V=int((state["radii"] > 0).sum().item()))
+                V=int((state["radii"] > 0).sum().item()), step_ms=step_ms)
 
 
-def cpu_oracle_sample(P, W, H, stride=4):
-    """Bounded CPU sample: full preprocess + binning, render fwd+bwd on every `stride`-th tile in
-    x and y; throughput extrapolated as P / (t_bin + stride^2 * t_render)."""
+def step_stats(step_ms):
+    return {"median": float(np.median(step_ms)), "p10": float(np.percentile(step_ms, 10)), "p90": float(np.percentile(step_ms, 90)),
+            "n": len(step_ms)}
+
+
+def cpu_oracle_full(P, W, H, stride=4):
+    """CPU port (oracle/liborc.so, OpenMP on all host threads) on the SAME workload: the full frame once (preprocess +
+    binning + render fwd+bwd of every tile) and, for comparison with round 1, the 1/stride^2 tile sample with its
+    extrapolation rule.  Also returns K_eval of the full frame (reference definition)."""
     import synth
     from oracle.oracle import SurfelOracle
     sc = synth.make_scene(P, W, H, seed=0)
@@ -315,32 +329,46 @@ def cpu_oracle_sample(P, W, H, stride=4):
     o.forward(sc.cam, sc.means3D, sc.opacities, sc.scales, sc.rotations, colors=sc.colors, tile_stride=1 << 20)
     t_bin = time.perf_counter() - t0
     t0 = time.perf_counter()
-    f = o.forward(sc.cam, sc.means3D, sc.opacities, sc.scales, sc.rotations, colors=sc.colors, tile_stride=stride)
+    o.forward(sc.cam, sc.means3D, sc.opacities, sc.scales, sc.rotations, colors=sc.colors, tile_stride=stride)
     o.backward(gc, go, tile_stride=stride)
-    t_all = time.perf_counter() - t0
-    t_render = max(t_all - t_bin, 1e-9)
-    est = t_bin + stride * stride * t_render
-    return dict(value=P / est, cores=os.cpu_count(), t_bin=t_bin, t_render_sample=t_render,
-                sample=f"oracle/liborc.so (OpenMP, {os.cpu_count()} threads): full preprocess+binning of the "
-                       f"{P}-surfel scene ({t_bin:.1f}s) + render fwd+bwd on every {stride}th tile in x and y "
-                       f"({t_render:.1f}s); Gaussians/s = P / (t_bin + {stride * stride} * t_render)",
-                R=f["num_rendered"])
+    t_sample = max(time.perf_counter() - t0 - t_bin, 1e-9)
+    t0 = time.perf_counter()
+    f = o.forward(sc.cam, sc.means3D, sc.opacities, sc.scales, sc.rotations, colors=sc.colors)
+    o.backward(gc, go)
+    t_full = time.perf_counter() - t0
+    est = t_bin + stride * stride * t_sample
+    return dict(value=P / t_full, cores=os.cpu_count(), t_full=t_full, k_eval=int(f["k_eval"]), R=int(f["num_rendered"]),
+                sample=f"oracle/liborc.so (OpenMP, {os.cpu_count()} threads) on the full workload once: forward+backward of "
+                       f"the {P}-surfel scene, every tile, {t_full:.1f}s (preprocess+binning {t_bin:.1f}s of it); the every-"
+                       f"{stride}th-tile sample of round 1 extrapolates to {est:.1f}s ({P / est:.0f} Gaussians/s)")
 
 
 def train_iters(impl):
     """Second half of BASELINE's metric ("train iters/s") on BASELINE config 2 (cfg-A: 2DGS, 100k surfels, 800x800, SH 3):
     the GS-SR-style iteration of tests/train_harness.py (render + post-processing + L1/SSIM/normal/dist losses + backward +
-    densification statistics + Adam, loss.item() every step).  Our arm uses the drop-in rasterizer and the fused SSIM /
-    post-processing ops; the reference arm uses the unmodified reference kernels and the reference's torch ops."""
+    densification statistics + Adam, loss.item() every step).  `value` = our arm with the drop-in rasterizer AND the fused
+    SSIM / post-processing ops; `rasterizer_only` = the same iteration with the reference's torch ops around the drop-in
+    rasterizer, which isolates the extension.  The reference arm runs the unmodified reference kernels + torch ops."""
     from train_harness import measure_iters_per_s
     ours = impl == "ours"
-    v, _ = measure_iters_per_s("ours" if ours else "reference", 100_000, 800, 800, iters=40, warmup=5,
-                               fused_ssim=ours, fused_post=ours)
-    return {"metric": "train iters/s", "value": v, "unit": "iters/s",
-            "workload": "2DGS iteration, P=100000 synthetic surfels, 800x800, SH degree 3 (BASELINE config 2), Adam, "
-                        "loss.item() per step; tests/train_harness.py",
-            "ops": "drop-in rasterizer + fused SSIM + fused post-processing" if ours else
-                   "reference CUDA rasterizer + reference torch ops"}
+    arm = "ours" if ours else "reference"
+    v, _ = measure_iters_per_s(arm, 100_000, 800, 800, iters=40, warmup=5, fused_ssim=ours, fused_post=ours)
+    out = {"metric": "train iters/s", "value": v, "unit": "iters/s",
+           "workload": "2DGS iteration, P=100000 synthetic surfels, 800x800, SH degree 3 (BASELINE config 2), Adam, "
+                       "loss.item() per step; tests/train_harness.py",
+           "ops": "drop-in rasterizer + fused SSIM + fused post-processing" if ours else
+                  "reference CUDA rasterizer + reference torch ops"}
+    if ours:
+        v2, _ = measure_iters_per_s("ours", 100_000, 800, 800, iters=40, warmup=5, fused_ssim=False, fused_post=False)
+        out["rasterizer_only"] = {"value": v2, "unit": "iters/s", "ops": "drop-in rasterizer + the reference's torch ops"}
+    for name, kw in (("config3_scaffold2dgs", dict(P=400_000, W=1600, H=1060, scaffold=True)),
+                     ("config4_pgsr", dict(P=1_000_000, W=1600, H=900, pgsr=True))):
+        try:
+            vv, _ = measure_iters_per_s(arm, iters=15, warmup=3, fused_ssim=ours, fused_post=ours, **kw)
+            out[name] = {"value": vv, "unit": "iters/s"}
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 
 def main():
@@ -354,6 +382,7 @@ def main():
     ap.add_argument("--H", type=int, default=H_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -389,13 +418,17 @@ def main():
                                               "sample": "the reference has no CPU path: its own UNMODIFIED CUDA "
                                                         "kernels (diff-surfel-rasterization compiled for sm_100a "
                                                         "by oracle/build_ref.sh) on the full workload on the GPU"},
-                             "stats": {"num_rendered": r["R"], "visible": r["V"]}, "gpu_launches": 0})
+                             "stats": {"num_rendered": r["R"], "visible": r["V"]}, "gpu_launches": 0,
+                             "step_ms": step_stats(r["step_ms"])})
                 if world == 1 and not args.no_train:
                     base["train"] = train_iters("reference")
+                if world == 1 and not args.no_extras:
+                    import bench_extras
+                    base["extras"] = bench_extras.run_all("reference")
                 print(json.dumps(base))
         else:
             if rank == 0:
-                c = cpu_oracle_sample(args.P, args.W, args.H)
+                c = cpu_oracle_full(args.P, args.W, args.H)
                 base.update({"impl": "reference", "value": c["value"], "ms_per_step": args.P / c["value"] * 1e3,
                              "n_gpus": 1, "e2e": {"value": c["value"], "unit": "Gaussians/s", "h2d_bytes_per_step": 0,
                                                   "d2h_bytes_per_step": 0},
@@ -429,15 +462,23 @@ def main():
                          "whole_step_frac": ab["whole_step"] / (r["ms_resident"] / args.steps * 1e-3) / 1e9 / peak,
                          "side_bound": issue_side_bound(dom, r["kernel_ms"][dom], (r["clocks"] or {}).get("sm_mhz"),
                                                         (args.P, args.W, args.H) == (P_DEFAULT, W_DEFAULT, H_DEFAULT))},
-            "kernel_ms": r["kernel_ms"],
+            "kernel_ms": r["kernel_ms"], "step_ms": step_stats(r["step_ms"]),
             "stats": {"num_rendered": R, "visible": r["V"], "pixels": N, "checksum": r["checksum"]},
         })
         if world == 1 and not args.no_train:
             base["train"] = train_iters("ours")
+        if world == 1 and not args.no_extras:
+            import bench_extras
+            base["extras"] = bench_extras.run_all("ours")
         if world == 1 and not args.no_cpu_baseline:
-            c = cpu_oracle_sample(args.P, args.W, args.H)
+            c = cpu_oracle_full(args.P, args.W, args.H)
             base["cpu_baseline"] = {"value": c["value"], "unit": "Gaussians/s", "cores": c["cores"], "kind": "port",
                                     "sample": c["sample"]}
+            step_s = r["ms_resident"] / args.steps * 1e-3
+            base["evals"] = {"k_eval": c["k_eval"], "evals_per_s": c["k_eval"] / step_s, "unit": "(pixel, splat) evaluations/s",
+                             "definition": "K_eval = sum over tiles of 256 x list entries walked before the whole block is done "
+                                           "(what the reference kernel evaluates, counted by the CPU port on rank 0's scene); "
+                                           "ours skips the culled share of them"}
         print(json.dumps(base))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <chrono>
+#include <mutex>
 #include "common.cuh"
 #include "ewa_common.cuh"
 #include "../../include/gsr_b200.h"
@@ -22,18 +24,16 @@ __global__ void mark_visible_kernel(int, const float*, const ViewParams, uint8_t
 cudaError_t launch_sh_forward(int, int, int, const float*, const float*, const float*, const int*, float*, uint8_t*, cudaStream_t);
 cudaError_t launch_sh_backward(int, int, int, const float*, const float*, const float*, const uint8_t*, const int*, const float*,
                                float*, float*, cudaStream_t);
-__global__ void tile_scan(int, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, const int*);
+__global__ void tile_scan(int, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, const int*, uint32_t, volatile uint32_t*, uint32_t);
 __global__ void scatter_keys(int, const float*, const float*, int, const CullRec*, const float*, const int*,
-                             const uint32_t*, int, int, uint32_t*, uint64_t*);
+                             const uint32_t*, int, int, uint32_t*, uint64_t*, uint32_t);
 __global__ void sort_build_records(const uint32_t*, uint64_t*, const GeomRec*, const float*, int, int, int, float4*,
                                    size_t, int);
 template <bool MARK>
 __global__ void surfel_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float*,
                                   uint32_t*, float*, float*, float4*);
-template <bool USED>
-__global__ void surfel_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*,
-                                  const float*, const uint32_t*, const float*, const float*, float*);
-int bwd_ctas_per_tile();
+cudaError_t launch_surfel_render_bwd(bool, int, const uint32_t*, const float4*, size_t, int, int, int, const float*, const float*,
+                                     const uint32_t*, const float*, const float*, float*, cudaStream_t);
 int fwd_ctas_per_tile();
 int ewa_bwd_ctas_per_tile();
 template <bool kRadiiOnly>
@@ -53,6 +53,10 @@ __global__ void ewa_render_fwd(const uint32_t*, const float4*, size_t, int, int,
 template <int MODE, bool USED>
 __global__ void ewa_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
                                const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+cudaError_t launch_surfel_audit(int, const uint32_t*, const float4*, size_t, int, int, int, const float*, const uint32_t*, uint32_t,
+                                float*, int*, int*, cudaStream_t);
+cudaError_t launch_ewa_audit(int, const uint32_t*, const float4*, size_t, int, int, int, const float*, const uint32_t*, uint32_t,
+                             float*, int*, int*, cudaStream_t);
 // ---- error string -------------------------------------------------------------
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -125,7 +129,6 @@ static ViewParams make_view(const float* view, const float* proj, const float* c
 }
 
 // ---- runtime options (debug / measurement only; defaults are the product path) ----
-static int g_last_R = 0;      // num_rendered of the previous forward (sizing guess only)
 static int g_no_used_bits = 0;   // 1: never use the forward's "blended" bits (the path taken when P >= 2^23)
 static int g_dbg = 0;         // developer timing experiments (results invalid when non-zero)
 static int g_no_cull = -1;   // 1: contribution boxes disabled (every pair evaluated, as the reference does)
@@ -153,6 +156,92 @@ struct HostTimer {
     }
     void flush(const char* what) { if (on) fprintf(stderr, "[gsr host] %s:%s\n", what, buf); }
 };
+
+// ---- num_rendered without blocking the stream -------------------------------------------------
+// The reference sizes its binning buffer from a blocking read-back of num_rendered in the middle of the forward
+// (S/cuda_rasterizer/rasterizer_impl.cu:278-285): the GPU idles while the host waits, allocates and launches the rest.
+// Here the host lays the buffer out for a capacity predicted from earlier frames of the same (device, rasterizer
+// family, resolution), enqueues ALL forward kernels (they clamp their lists to the capacity), and only then waits
+// for R, which tile_scan publishes into a pinned, mapped host slot -- by then the GPU is busy with the rest of the
+// forward, so nothing idles and no cudaStreamSynchronize / cudaMemcpy is issued.  R <= capacity (the steady state):
+// done.  R > capacity, or no history yet: the binning buffer is requested again with the exact size and tile_scan /
+// scatter / sort / render are re-enqueued behind the clamped run -- still without a stream sync; outputs are simply
+// overwritten.  The value returned to the caller (and passed back to the backward as R) is the capacity the buffer was
+// laid out for; the true count is available from gsr_last_num_rendered().
+struct RHistEntry { int dev, family, W, H; double hist; uint64_t stamp; };
+static std::mutex g_hist_mu;
+static RHistEntry g_hist[32];
+static int g_hist_n = 0;
+static uint64_t g_hist_clock = 0;
+static int g_force_cap = 0;                      // option "force_capacity": tests of the overflow path
+static thread_local int g_true_R = 0;
+
+static uint32_t predicted_capacity(int dev, int family, int W, int H) {
+    if (g_force_cap > 0) return (uint32_t)g_force_cap;
+    std::lock_guard<std::mutex> lk(g_hist_mu);
+    for (int i = 0; i < g_hist_n; i++) {
+        RHistEntry& e = g_hist[i];
+        if (e.dev == dev && e.family == family && e.W == W && e.H == H) {
+            e.stamp = ++g_hist_clock;
+            const double c = fmin(2.0e9, 1.25 * e.hist + 4096.0);
+            return (uint32_t)((((uint64_t)c + 4095) / 4096) * 4096);
+        }
+    }
+    return 0;   // no history: the caller waits for R first
+}
+static void record_num_rendered(int dev, int family, int W, int H, uint32_t R) {
+    std::lock_guard<std::mutex> lk(g_hist_mu);
+    int slot = -1;
+    for (int i = 0; i < g_hist_n; i++)
+        if (g_hist[i].dev == dev && g_hist[i].family == family && g_hist[i].W == W && g_hist[i].H == H) slot = i;
+    if (slot < 0) {
+        if (g_hist_n < 32) slot = g_hist_n++;
+        else { slot = 0; for (int i = 1; i < 32; i++) if (g_hist[i].stamp < g_hist[slot].stamp) slot = i; }   // least recently used
+        g_hist[slot] = {dev, family, W, H, 0.0, 0};
+    }
+    // slowly decaying maximum: alternating near / far cameras keep the larger layout, a shrinking scene lets go of it
+    g_hist[slot].hist = fmax((double)R, 0.97 * g_hist[slot].hist);
+    g_hist[slot].stamp = ++g_hist_clock;
+}
+
+// pinned, mapped, portable host words: slot = {sequence number, R, prefiltered flag, -}; one slot per host thread
+static uint32_t* g_slots = nullptr;
+static std::atomic<int> g_slot_next{0};
+static std::mutex g_slot_mu;
+static volatile uint32_t* my_host_slot() {
+    thread_local volatile uint32_t* mine = nullptr;
+    if (mine) return mine;
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    if (!g_slots) {
+        if (cudaHostAlloc((void**)&g_slots, 256 * 16, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        memset(g_slots, 0, 256 * 16);
+    }
+    mine = g_slots + 4 * (g_slot_next.fetch_add(1) % 256);
+    return mine;
+}
+static thread_local uint32_t g_seq = 0;
+
+// Wait until tile_scan has published sequence number `seq`; rb = {R, prefiltered flag}.  Pure host-memory polling;
+// the stream is queried now and then so that a faulted kernel turns into an error instead of a hang.
+static int wait_num_rendered(volatile uint32_t* slot, uint32_t seq, cudaStream_t s, uint32_t rb[2]) {
+    for (uint64_t spins = 1;; spins++) {
+        if (slot[0] == seq) break;
+        if ((spins & 0x3fff) == 0) {
+            const cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaSuccess && e != cudaErrorNotReady) { set_error("forward kernels failed: %s", cudaGetErrorString(e)); return GSR_E_CUDA; }
+            if (e == cudaSuccess && slot[0] != seq) {
+                std::atomic_thread_fence(std::memory_order_seq_cst);
+                if (slot[0] != seq) { set_error("tile_scan finished without publishing num_rendered"); return GSR_E_CUDA; }
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    rb[0] = slot[1]; rb[1] = slot[2];
+    return GSR_OK;
+}
 
 // ---- per-kernel device timing (cudaEvents on the caller's stream, off by default) ----
 // bench.py needs the dominant kernel's duration measured live, outside any profiler.
@@ -182,9 +271,12 @@ int gsr_set_option(const char* name, int value) {
     if (!strcmp(name, "no_cull")) { g_no_cull = value ? 1 : 0; return GSR_OK; }
     if (!strcmp(name, "dbg")) { g_dbg = value; return GSR_OK; }
     if (!strcmp(name, "no_used_bits")) { g_no_used_bits = value ? 1 : 0; return GSR_OK; }
+    if (!strcmp(name, "force_capacity")) { g_force_cap = value > 0 ? value : 0; return GSR_OK; }
     set_error("gsr_set_option: unknown option %s", name);
     return GSR_E_INVALID;
 }
+
+int gsr_last_num_rendered(void) { return g_true_R; }
 
 int gsr_profile_enable(int on) {
     if (on && !g_prof.created) {
@@ -263,72 +355,91 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         if (shs) GSR_CUDA_CHECK(launch_sh_forward(P, D, M, means3D, cam_pos, shs, radii, gw.rgb, gw.clamped, s));
         prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
-        prof_begin(GSR_PROF_SCAN, s);
-        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total,
-                                     gw.flags);
-        prof_end(GSR_PROF_SCAN, s);
-        GSR_CUDA_CHECK(cudaGetLastError());
         ht.mark("launch_pre");
-        // Speculative binning buffer: ask for last call's R (+25%) BEFORE blocking on the read-back, so
-        // that in steady state nothing but three kernel launches stands between the read-back and
-        // the GPU resuming.  A second, exact request follows only when the guess was too small.
-        const int R_guess = g_last_R > 0 ? (int)fmin(2.0e9, 1.25 * (double)g_last_R + 4096.0) : 0;
-        char* bbase = nullptr;
-        size_t bcap = 0;
-        if (R_guess > 0) {
-            bcap = BinWs::carve(bw, nullptr, R_guess, P);
-            bbase = binningBuffer(user, bcap);
-            if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bcap); return GSR_E_ALLOC; }
-        }
-        ht.mark("binbuf_spec");
-        // num_rendered sizes the binning buffer: the same single read-back as the reference
-        // (S/rasterizer_impl.cu:282); the prefiltered flag rides along.
-        uint32_t rb[2] = {0u, 0u};
-        GSR_CUDA_CHECK(cudaMemcpyAsync(rb, iw.total, 8, cudaMemcpyDeviceToHost, s));
-        GSR_CUDA_CHECK(cudaStreamSynchronize(s));
-        if (rb[1]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
-        if (rb[0] > 0x7fffff00u) { set_error("num_rendered overflow (%u)", rb[0]); return GSR_E_OVERFLOW; }
-        R = (int)rb[0];
-        g_last_R = R;
-        ht.mark("sync_R");
-        size_t bbytes = BinWs::carve(bw, nullptr, R, P);
-        if (!bbase || bbytes > bcap) {
-            bbase = binningBuffer(user, bbytes);
-            if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
-        }
-        BinWs::carve(bw, align256(bbase), R, P);
-        ht.mark("binbuf");
-    } else {
-        size_t bbytes = BinWs::carve(bw, nullptr, 0, 0);
-        char* bbase = binningBuffer(user, bbytes);
-        if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
-        BinWs::carve(bw, align256(bbase), 0, 0);
     }
 
-    if (R > 0) {
-        prof_begin(GSR_PROF_DUPLICATE, s);
-        scatter_keys<<<(P + 255) / 256, 256, 0, s>>>(P, &gw.geom->tu.w, &gw.geom->tv.w, (int)(sizeof(GeomRec) / 4), gw.cull,
-                                                     gw.depths, radii, gw.masks, vc.gx, vc.gy, iw.tile_cursor, bw.keys);
-        prof_end(GSR_PROF_DUPLICATE, s);
+    // binning + render for a buffer laid out for `cap` entries (see "num_rendered without blocking the stream")
+    auto lay_out = [&](uint32_t cap) -> int {
+        const size_t bbytes = BinWs::carve(bw, nullptr, (int64_t)cap, P);
+        char* bbase = binningBuffer(user, bbytes);
+        if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
+        BinWs::carve(bw, align256(bbase), (int64_t)cap, P);
+        return GSR_OK;
+    };
+    auto scan = [&](uint32_t cap, volatile uint32_t* slot, uint32_t seq) -> int {
+        prof_begin(GSR_PROF_SCAN, s);
+        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total, gw.flags, cap, slot, seq);
+        prof_end(GSR_PROF_SCAN, s);
         GSR_CUDA_CHECK(cudaGetLastError());
-        const float* colors = colors_precomp ? colors_precomp : gw.rgb;
-        prof_begin(GSR_PROF_BUILD_RECORDS, s);
-        sort_build_records<<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, vc.gx, W, H,
-                                                  bw.planes, bw.plane_stride, g_dbg);
-        prof_end(GSR_PROF_BUILD_RECORDS, s);
+        return GSR_OK;
+    };
+    auto bin_and_render = [&](uint32_t cap) -> int {
+        if (P > 0 && cap > 0) {
+            prof_begin(GSR_PROF_DUPLICATE, s);
+            scatter_keys<<<(P + 255) / 256, 256, 0, s>>>(P, &gw.geom->tu.w, &gw.geom->tv.w, (int)(sizeof(GeomRec) / 4), gw.cull,
+                                                         gw.depths, radii, gw.masks, vc.gx, vc.gy, iw.tile_cursor, bw.keys, cap);
+            prof_end(GSR_PROF_DUPLICATE, s);
+            GSR_CUDA_CHECK(cudaGetLastError());
+            const float* colors = colors_precomp ? colors_precomp : gw.rgb;
+            prof_begin(GSR_PROF_BUILD_RECORDS, s);
+            sort_build_records<<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, vc.gx, W, H,
+                                                      bw.planes, bw.plane_stride, g_dbg);
+            prof_end(GSR_PROF_BUILD_RECORDS, s);
+            GSR_CUDA_CHECK(cudaGetLastError());
+        }
+        prof_begin(GSR_PROF_RENDER_FWD, s);
+        if (cap > 0 && P < (1 << REC_USED_SHIFT) && !g_no_used_bits)
+            surfel_render_fwd<true><<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(
+                iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, out_color, out_others,
+                bw.planes + 3 * bw.plane_stride);
+        else
+            surfel_render_fwd<false><<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(
+                iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, out_color, out_others,
+                nullptr);
+        prof_end(GSR_PROF_RENDER_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
+        return GSR_OK;
+    };
+
+    uint32_t layout = 0;     // entries the binning buffer is laid out for == the value handed back to the caller
+    if (P > 0) {
+        int dev = 0;
+        GSR_CUDA_CHECK(cudaGetDevice(&dev));
+        volatile uint32_t* slot = my_host_slot();
+        if (!slot) { set_error("cudaHostAlloc of the num_rendered slot failed"); return GSR_E_CUDA; }
+        const uint32_t seq = ++g_seq;
+        const uint32_t cap = predicted_capacity(dev, 0, W, H);
+        int rc;
+        if (cap > 0) {
+            if ((rc = lay_out(cap)) < 0) return rc;
+            if ((rc = scan(cap, slot, seq)) < 0) return rc;
+            if ((rc = bin_and_render(cap)) < 0) return rc;
+            ht.mark("launch_spec");
+        } else {
+            if ((rc = scan(0xffffffffu, slot, seq)) < 0) return rc;
+        }
+        uint32_t rb[2] = {0u, 0u};
+        if ((rc = wait_num_rendered(slot, seq, s, rb)) < 0) return rc;
+        ht.mark("wait_R");
+        if (rb[1]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
+        if (rb[0] > 0x7fffff00u) { set_error("num_rendered overflow (%u)", rb[0]); return GSR_E_OVERFLOW; }
+        g_true_R = (int)rb[0];
+        if (g_force_cap <= 0) record_num_rendered(dev, 0, W, H, rb[0]);
+        layout = cap;
+        if (cap == 0 || rb[0] > cap) {
+            // first frame of this configuration, or more pairs than predicted: exact layout, re-enqueue behind the clamped run
+            layout = rb[0];
+            if ((rc = lay_out(layout)) < 0) return rc;
+            if (cap > 0 && (rc = scan(0xffffffffu, nullptr, 0)) < 0) return rc;
+            if ((rc = bin_and_render(layout)) < 0) return rc;
+        }
+    } else {
+        int rc;
+        g_true_R = 0;
+        if ((rc = lay_out(0)) < 0) return rc;
+        if ((rc = bin_and_render(0)) < 0) return rc;
     }
-    prof_begin(GSR_PROF_RENDER_FWD, s);
-    if (R > 0 && P < (1 << REC_USED_SHIFT) && !g_no_used_bits)
-        surfel_render_fwd<true><<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(
-            iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, out_color, out_others,
-            bw.planes + 3 * bw.plane_stride);
-    else
-        surfel_render_fwd<false><<<ntiles * fwd_ctas_per_tile(), 256 / fwd_ctas_per_tile(), 0, s>>>(
-            iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, out_color, out_others,
-            nullptr);
-    prof_end(GSR_PROF_RENDER_FWD, s);
-    GSR_CUDA_CHECK(cudaGetLastError());
+    R = (int)layout;
     (void)N;
     ht.mark("launch_rest");
     ht.flush("forward");
@@ -367,12 +478,9 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
     GSR_CUDA_CHECK(cudaMemsetAsync(bw.gacc, 0, (size_t)P * GACC_STRIDE * sizeof(float), s));
     if (R > 0) {
         prof_begin(GSR_PROF_RENDER_BWD, s);
-        if (P < (1 << REC_USED_SHIFT) && !g_no_used_bits)
-            surfel_render_bwd<true><<<ntiles * bwd_ctas_per_tile(), 256 / bwd_ctas_per_tile(), 0, s>>>(
-                iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, dL_dpix, dL_dothers, bw.gacc);
-        else
-            surfel_render_bwd<false><<<ntiles * bwd_ctas_per_tile(), 256 / bwd_ctas_per_tile(), 0, s>>>(
-                iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, dL_dpix, dL_dothers, bw.gacc);
+        GSR_CUDA_CHECK(launch_surfel_render_bwd(P < (1 << REC_USED_SHIFT) && !g_no_used_bits, ntiles, iw.tile_offset, bw.planes,
+                                                bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, dL_dpix,
+                                                dL_dothers, bw.gacc, s));
         prof_end(GSR_PROF_RENDER_BWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }
@@ -406,7 +514,6 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 
 // ---- EWA family (3DGS + PGSR plane): shared host orchestration ------------------------------------
 namespace gsr {
-static int g_last_R_ewa = 0;
 
 struct EwaFwdArgs {
     gsr_buffer_fn geometryBuffer, binningBuffer, imageBuffer;
@@ -479,60 +586,88 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
         if (a.shs) GSR_CUDA_CHECK(launch_sh_forward(P, a.D, a.M, a.means3D, a.cam_pos, a.shs, a.radii, gw.rgb, gw.clamped, s));
         prof_end(GSR_PROF_PREPROCESS_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
-        prof_begin(GSR_PROF_SCAN, s);
-        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total, gw.flags);
-        prof_end(GSR_PROF_SCAN, s);
-        GSR_CUDA_CHECK(cudaGetLastError());
-        // speculative binning buffer before the read-back (see gsr_surfel_forward)
-        const int R_guess = g_last_R_ewa > 0 ? (int)fmin(2.0e9, 1.25 * (double)g_last_R_ewa + 4096.0) : 0;
-        char* bbase = nullptr;
-        size_t bcap = 0;
-        if (R_guess > 0) {
-            bcap = BinWs::carve(bw, nullptr, R_guess, P, nplanes, EWA_GACC);
-            bbase = a.binningBuffer(a.user, bcap);
-            if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bcap); return GSR_E_ALLOC; }
-        }
-        uint32_t rb[2] = {0u, 0u};
-        GSR_CUDA_CHECK(cudaMemcpyAsync(rb, iw.total, 8, cudaMemcpyDeviceToHost, s));
-        GSR_CUDA_CHECK(cudaStreamSynchronize(s));
-        if (rb[1]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
-        if (rb[0] > 0x7fffff00u) { set_error("num_rendered overflow (%u)", rb[0]); return GSR_E_OVERFLOW; }
-        R = (int)rb[0];
-        g_last_R_ewa = R;
-        size_t bbytes = BinWs::carve(bw, nullptr, R, P, nplanes, EWA_GACC);
-        if (!bbase || bbytes > bcap) {
-            bbase = a.binningBuffer(a.user, bbytes);
-            if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
-        }
-        BinWs::carve(bw, align256(bbase), R, P, nplanes, EWA_GACC);
-    } else {
-        size_t bbytes = BinWs::carve(bw, nullptr, 0, 0, nplanes, EWA_GACC);
+    }
+
+    // binning + render for a buffer laid out for `cap` entries (see "num_rendered without blocking the stream")
+    auto lay_out = [&](uint32_t cap) -> int {
+        const size_t bbytes = BinWs::carve(bw, nullptr, (int64_t)cap, P, nplanes, EWA_GACC);
         char* bbase = a.binningBuffer(a.user, bbytes);
         if (!bbase) { set_error("binningBuffer callback failed (%zu bytes)", bbytes); return GSR_E_ALLOC; }
-        BinWs::carve(bw, align256(bbase), 0, 0, nplanes, EWA_GACC);
-    }
-    if (R > 0) {
-        prof_begin(GSR_PROF_DUPLICATE, s);
-        scatter_keys<<<(P + 255) / 256, 256, 0, s>>>(P, &gw.geom->a.x, &gw.geom->a.y, (int)(sizeof(EwaGeom) / 4), gw.cull,
-                                                     gw.depths, a.radii, gw.masks, vc.gx, vc.gy, iw.tile_cursor, bw.keys);
-        prof_end(GSR_PROF_DUPLICATE, s);
+        BinWs::carve(bw, align256(bbase), (int64_t)cap, P, nplanes, EWA_GACC);
+        return GSR_OK;
+    };
+    auto scan = [&](uint32_t cap, volatile uint32_t* slot, uint32_t seq) -> int {
+        prof_begin(GSR_PROF_SCAN, s);
+        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total, gw.flags, cap, slot, seq);
+        prof_end(GSR_PROF_SCAN, s);
         GSR_CUDA_CHECK(cudaGetLastError());
-        const float* colors = a.colors_precomp ? a.colors_precomp : gw.rgb;
-        prof_begin(GSR_PROF_BUILD_RECORDS, s);
-        if (a.geo) ewa_build_records<true><<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, a.all_map, vc.gx, bw.planes, bw.plane_stride);
-        else ewa_build_records<false><<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, nullptr, vc.gx, bw.planes, bw.plane_stride);
-        prof_end(GSR_PROF_BUILD_RECORDS, s);
+        return GSR_OK;
+    };
+    auto bin_and_render = [&](uint32_t cap, bool again) -> int {
+        if (P > 0 && cap > 0) {
+            prof_begin(GSR_PROF_DUPLICATE, s);
+            scatter_keys<<<(P + 255) / 256, 256, 0, s>>>(P, &gw.geom->a.x, &gw.geom->a.y, (int)(sizeof(EwaGeom) / 4), gw.cull,
+                                                         gw.depths, a.radii, gw.masks, vc.gx, vc.gy, iw.tile_cursor, bw.keys, cap);
+            prof_end(GSR_PROF_DUPLICATE, s);
+            GSR_CUDA_CHECK(cudaGetLastError());
+            const float* colors = a.colors_precomp ? a.colors_precomp : gw.rgb;
+            prof_begin(GSR_PROF_BUILD_RECORDS, s);
+            if (a.geo) ewa_build_records<true><<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, a.all_map, vc.gx, bw.planes, bw.plane_stride);
+            else ewa_build_records<false><<<ntiles, 256, 0, s>>>(iw.tile_offset, bw.keys, gw.geom, colors, nullptr, vc.gx, bw.planes, bw.plane_stride);
+            prof_end(GSR_PROF_BUILD_RECORDS, s);
+            GSR_CUDA_CHECK(cudaGetLastError());
+        }
+        // out_observe is accumulated with atomics by the render kernel: a re-run starts from zero again
+        if (again && a.plane && P > 0) GSR_CUDA_CHECK(cudaMemsetAsync(a.out_observe, 0, (size_t)P * sizeof(int), s));
+        prof_begin(GSR_PROF_RENDER_FWD, s);
+        // plane 1 holds the idx|flag word that receives the forward's "blended" marks (P < 2^23)
+        float4* mark = (cap > 0 && P < (1 << REC_USED_SHIFT) && !g_no_used_bits) ? bw.planes + 1 * bw.plane_stride : nullptr;
+        if (a.geo) ewa_render_fwd<true><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+                                                                    iw.final_T, iw.n_contrib, a.out_color, a.out_observe, a.out_all_map, a.out_plane_depth, mark);
+        else ewa_render_fwd<false><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
+                                                               iw.final_T, iw.n_contrib, a.out_color, a.plane ? a.out_observe : nullptr, nullptr, nullptr, mark);
+        prof_end(GSR_PROF_RENDER_FWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
+        return GSR_OK;
+    };
+
+    uint32_t layout = 0;
+    if (P > 0) {
+        int dev = 0;
+        GSR_CUDA_CHECK(cudaGetDevice(&dev));
+        volatile uint32_t* slot = my_host_slot();
+        if (!slot) { set_error("cudaHostAlloc of the num_rendered slot failed"); return GSR_E_CUDA; }
+        const uint32_t seq = ++g_seq;
+        const int family = a.geo ? 3 : (a.plane ? 2 : 1);
+        const uint32_t cap = predicted_capacity(dev, family, W, H);
+        int rc;
+        if (cap > 0) {
+            if ((rc = lay_out(cap)) < 0) return rc;
+            if ((rc = scan(cap, slot, seq)) < 0) return rc;
+            if ((rc = bin_and_render(cap, false)) < 0) return rc;
+        } else {
+            if ((rc = scan(0xffffffffu, slot, seq)) < 0) return rc;
+        }
+        uint32_t rb[2] = {0u, 0u};
+        if ((rc = wait_num_rendered(slot, seq, s, rb)) < 0) return rc;
+        if (rb[1]) { set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return GSR_E_PREFILTERED; }
+        if (rb[0] > 0x7fffff00u) { set_error("num_rendered overflow (%u)", rb[0]); return GSR_E_OVERFLOW; }
+        g_true_R = (int)rb[0];
+        if (g_force_cap <= 0) record_num_rendered(dev, family, W, H, rb[0]);
+        layout = cap;
+        if (cap == 0 || rb[0] > cap) {
+            layout = rb[0];
+            if ((rc = lay_out(layout)) < 0) return rc;
+            if (cap > 0 && (rc = scan(0xffffffffu, nullptr, 0)) < 0) return rc;
+            if ((rc = bin_and_render(layout, cap > 0)) < 0) return rc;
+        }
+    } else {
+        int rc;
+        g_true_R = 0;
+        if ((rc = lay_out(0)) < 0) return rc;
+        if ((rc = bin_and_render(0, false)) < 0) return rc;
     }
-    prof_begin(GSR_PROF_RENDER_FWD, s);
-    // plane 1 holds the idx|flag word that receives the forward's "blended" marks (P < 2^23)
-    float4* mark = (R > 0 && P < (1 << REC_USED_SHIFT) && !g_no_used_bits) ? bw.planes + 1 * bw.plane_stride : nullptr;
-    if (a.geo) ewa_render_fwd<true><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
-                                                                iw.final_T, iw.n_contrib, a.out_color, a.out_observe, a.out_all_map, a.out_plane_depth, mark);
-    else ewa_render_fwd<false><<<ntiles, TILE_PIX, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, focal_x, focal_y,
-                                                           iw.final_T, iw.n_contrib, a.out_color, a.plane ? a.out_observe : nullptr, nullptr, nullptr, mark);
-    prof_end(GSR_PROF_RENDER_FWD, s);
-    GSR_CUDA_CHECK(cudaGetLastError());
+    R = (int)layout;
     if (a.debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return R;
 }
@@ -703,6 +838,40 @@ int gsr_visible_filter(int P, int width, int height, const float* means3D, const
         tan_fovx, tan_fovy, false, true, radii, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     GSR_CUDA_CHECK(cudaGetLastError());
     if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    return GSR_OK;
+}
+
+int gsr_surfel_audit(int P, int R, int width, int height, char* binning_buffer, char* image_buffer, float* margins,
+                     int* info, int* mismatches, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0 || R < 0 || width <= 0 || height <= 0 || !binning_buffer || !image_buffer || !margins || !info || !mismatches) {
+        set_error("gsr_surfel_audit: invalid argument"); return GSR_E_INVALID;
+    }
+    const ViewParams vc = make_view(nullptr, nullptr, nullptr, width, height, 1.0f);
+    ImageWs iw; BinWs bw;
+    ImageWs::carve(iw, align256(image_buffer), width, height);
+    BinWs::carve(bw, align256(binning_buffer), R, P);
+    const uint32_t idx_mask = (P < (1 << REC_USED_SHIFT) && !g_no_used_bits) ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS;
+    GSR_CUDA_CHECK(cudaMemsetAsync(mismatches, 0, sizeof(int), s));
+    GSR_CUDA_CHECK(launch_surfel_audit(vc.gx * vc.gy, iw.tile_offset, bw.planes, bw.plane_stride, width, height, vc.gx, iw.final_T,
+                                       iw.n_contrib, idx_mask, margins, info, mismatches, s));
+    return GSR_OK;
+}
+
+int gsr_ewa_audit(int P, int R, int width, int height, int render_geo, char* binning_buffer, char* image_buffer,
+                  float* margins, int* info, int* mismatches, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0 || R < 0 || width <= 0 || height <= 0 || !binning_buffer || !image_buffer || !margins || !info || !mismatches) {
+        set_error("gsr_ewa_audit: invalid argument"); return GSR_E_INVALID;
+    }
+    const ViewParams vc = make_view(nullptr, nullptr, nullptr, width, height, 1.0f);
+    ImageWs iw; BinWs bw;
+    ImageWs::carve(iw, align256(image_buffer), width, height, 1, 1);
+    BinWs::carve(bw, align256(binning_buffer), R, P, render_geo ? EWA_PLANES_GEO : EWA_PLANES, EWA_GACC);
+    const uint32_t idx_mask = (P < (1 << REC_USED_SHIFT) && !g_no_used_bits) ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS;
+    GSR_CUDA_CHECK(cudaMemsetAsync(mismatches, 0, sizeof(int), s));
+    GSR_CUDA_CHECK(launch_ewa_audit(vc.gx * vc.gy, iw.tile_offset, bw.planes, bw.plane_stride, width, height, vc.gx, iw.final_T,
+                                    iw.n_contrib, idx_mask, margins, info, mismatches, s));
     return GSR_OK;
 }
 

@@ -6,7 +6,8 @@
 // emitted in ascending Gaussian index produces.  The reference sorts all R pairs globally
 // (6 radix passes over 12-byte pairs); here the tile is known when a pair is emitted, so
 //   1. the forward preprocess counts pairs per tile (atomicAdd on a tiles-sized histogram),
-//   2. tile_scan turns counts into per-tile offsets (one CTA; also yields R),
+//   2. tile_scan turns counts into per-tile offsets (one CTA; also yields R, published to the host through a
+//      pinned slot so that the host never blocks the stream to learn it, see abi.cu),
 //   3. scatter_keys drops each pair's 64-bit (depth_bits << 32 | index) key into its tile's
 //      bucket (slot order inside a bucket is arbitrary -- the key is a total order),
 //   4. sort_build_records: one CTA per tile sorts its bucket with a bitonic network in shared
@@ -24,7 +25,12 @@ namespace gsr {
 // ---- 2. exclusive scan of per-tile counts (single CTA) -------------------------------------
 __global__ void __launch_bounds__(1024)
 tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-          uint32_t* __restrict__ cursors, uint32_t* __restrict__ total, const int* __restrict__ flags) {
+          uint32_t* __restrict__ cursors, uint32_t* __restrict__ total, const int* __restrict__ flags, uint32_t cap,
+          volatile uint32_t* host_slot, uint32_t seq) {
+    // cap = number of list entries the binning buffer was laid out for.  The host sizes that buffer BEFORE it knows R
+    // (from earlier frames), so the lists the later kernels see are clamped to it: offsets[] saturate at cap and
+    // scatter_keys drops entries at positions >= cap.  R itself goes to the host, which re-runs binning and rendering
+    // with an exact buffer in the (rare) case R > cap.
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -52,13 +58,20 @@ tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict_
         }
         __syncthreads();
         const uint32_t excl = carry + warp_sums[warp] + (x - v);
-        if (i < ntiles) { offsets[i] = excl; cursors[(size_t)i * TILE_CTR_STRIDE] = excl; }
+        if (i < ntiles) { offsets[i] = min(excl, cap); cursors[(size_t)i * TILE_CTR_STRIDE] = excl; }
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    // total[0] = R, total[1] = prefiltered-violation flag: one 8-byte read-back for the host
-    if (threadIdx.x == 0) { offsets[ntiles] = carry; total[0] = carry; total[1] = (uint32_t)flags[0]; }
+    // total[0] = R, total[1] = prefiltered-violation flag; the same two words + a sequence number go to the host slot
+    if (threadIdx.x == 0) {
+        offsets[ntiles] = min(carry, cap); total[0] = carry; total[1] = (uint32_t)flags[0];
+        if (host_slot != nullptr) {
+            host_slot[1] = carry; host_slot[2] = (uint32_t)flags[0];
+            __threadfence_system();
+            host_slot[0] = seq;
+        }
+    }
 }
 
 // ---- 3. scatter (depth, index) keys into tile buckets ---------------------------------------
@@ -66,7 +79,7 @@ __global__ void __launch_bounds__(256)
 scatter_keys(int P, const float* __restrict__ centre_x, const float* __restrict__ centre_y, int centre_stride,
              const CullRec* __restrict__ cull,
              const float* __restrict__ depths, const int* __restrict__ radii, const uint32_t* __restrict__ masks, int gx, int gy,
-             uint32_t* __restrict__ cursors, uint64_t* __restrict__ keys) {
+             uint32_t* __restrict__ cursors, uint64_t* __restrict__ keys, uint32_t cap) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     // all five per-Gaussian loads are issued together (one memory round trip; values of culled Gaussians are in
@@ -98,13 +111,16 @@ scatter_keys(int P, const float* __restrict__ centre_x, const float* __restrict_
             }
 #pragma unroll
             for (int u = 0; u < 4; u++)
-                if (u < cnt) keys[pos[u]] = key;
+                if (u < cnt && pos[u] < cap) keys[pos[u]] = key;
         }
     } else {
         const CullRec cr = cull[idx];
         for (int y = y0; y < y1; y++)
             for (int x = x0; x < x1; x++)
-                if (tile_may_contribute(cr, cx, cy, x, y)) keys[atomicAdd(&cursors[(size_t)(y * gx + x) * TILE_CTR_STRIDE], 1u)] = key;
+                if (tile_may_contribute(cr, cx, cy, x, y)) {
+                    const uint32_t pos = atomicAdd(&cursors[(size_t)(y * gx + x) * TILE_CTR_STRIDE], 1u);
+                    if (pos < cap) keys[pos] = key;
+                }
     }
 }
 

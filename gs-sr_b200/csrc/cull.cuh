@@ -11,13 +11,18 @@
 // exact for the continuous rectangle (hence conservative for the pixel centres inside it);
 // otherwise (the tau-disc of the splat reaches the camera plane) the caller must treat the
 // splat as "always evaluate".  tau carries slack for exp/log rounding and the rectangle is
-// widened by a quarter pixel, orders of magnitude above the float32 evaluation error.
+// widened by a quarter pixel.  That margin does NOT cover edge-on surfels: their conic is a sliver
+// whose coefficients are ~1e6 while q is only ~0.1 deep inside it, below float32 resolution of the
+// cancelling terms (found at cfg-B: one pair in 1e9, tests/test_fullsize_parity_gpu.py).  Every
+// comparison therefore carries an explicit rounding bound QUADRIC_EPS x (sum of the magnitudes of
+// the terms that cancel), so a decision that float32 cannot make reliably falls on "evaluate".
 #pragma once
 #include "common.cuh"
 
 namespace gsr {
 
 constexpr float CULL_MARGIN = 0.25f;
+constexpr float QUADRIC_EPS = 1e-6f;     // ~16 ulp: rounding bound, relative to the magnitude of the cancelling terms
 
 struct Quadric {           // q(x,y) = xx x^2 + 2 xy x y + yy y^2 + 2 bx x + 2 by y + c0
     float xx, xy, yy, bx, by, c0;
@@ -51,24 +56,30 @@ __device__ __forceinline__ float quadric_eval(const Quadric& q, float x, float y
     return (q.xx * x + 2.f * (q.xy * y + q.bx)) * x + (q.yy * y + 2.f * q.by) * y + q.c0;
 }
 
-// Ellipse {q <= 0} vs rectangle [x0,x1]x[y0,y1]; requires quadric_is_ellipse(q).
+// Ellipse {q <= 0} vs rectangle [x0,x1]x[y0,y1]; requires quadric_is_ellipse(q).  Conservative under float32
+// rounding: E bounds the absolute error of any evaluation of q inside the rectangle.
 __device__ __forceinline__ bool ellipse_hits_rect(const Quadric& q, float x0, float x1, float y0, float y1) {
+    const float X = fmaxf(fabsf(x0), fabsf(x1)), Y = fmaxf(fabsf(y0), fabsf(y1));
+    const float axy = fabsf(q.xy), abx = fabsf(q.bx), aby = fabsf(q.by);
+    const float E = QUADRIC_EPS * ((q.xx * X + 2.f * (axy * Y + abx)) * X + (q.yy * Y + 2.f * aby) * Y + fabsf(q.c0));
     const float det = q.xx * q.yy - q.xy * q.xy;            // > 0
     // centre e solves [xx xy; xy yy] e = -(bx, by); compare without dividing
     const float ex = q.xy * q.by - q.yy * q.bx, ey = q.xy * q.bx - q.xx * q.by;   // = det * centre
-    if (ex >= x0 * det && ex <= x1 * det && ey >= y0 * det && ey <= y1 * det) return true;
+    const float dm = QUADRIC_EPS * (q.xx * q.yy + q.xy * q.xy);                   // rounding of det (it cancels for rotated slivers)
+    const float tx = QUADRIC_EPS * (axy * aby + q.yy * abx) + X * dm, ty = QUADRIC_EPS * (axy * abx + q.xx * aby) + Y * dm;
+    if (ex >= x0 * det - tx && ex <= x1 * det + tx && ey >= y0 * det - ty && ey <= y1 * det + ty) return true;
     // corners
-    if (quadric_eval(q, x0, y0) <= 0.f || quadric_eval(q, x1, y0) <= 0.f || quadric_eval(q, x0, y1) <= 0.f ||
-        quadric_eval(q, x1, y1) <= 0.f) return true;
+    if (quadric_eval(q, x0, y0) <= E || quadric_eval(q, x1, y0) <= E || quadric_eval(q, x0, y1) <= E ||
+        quadric_eval(q, x1, y1) <= E) return true;
     // edges: interior minimum of the 1-D restriction  t -> A t^2 + 2 B t + C  is C - B^2/A at t* = -B/A
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const float yc = k ? y1 : y0;
         const float B = q.xy * yc + q.bx, C = (q.yy * yc + 2.f * q.by) * yc + q.c0;
-        if (-B > x0 * q.xx && -B < x1 * q.xx && C * q.xx <= B * B) return true;
+        if (-B > x0 * q.xx && -B < x1 * q.xx && C * q.xx <= B * B + (E * q.xx + QUADRIC_EPS * B * B)) return true;
         const float xc = k ? x1 : x0;
         const float B2 = q.xy * xc + q.by, C2 = (q.xx * xc + 2.f * q.bx) * xc + q.c0;
-        if (-B2 > y0 * q.yy && -B2 < y1 * q.yy && C2 * q.yy <= B2 * B2) return true;
+        if (-B2 > y0 * q.yy && -B2 < y1 * q.yy && C2 * q.yy <= B2 * B2 + (E * q.yy + QUADRIC_EPS * B2 * B2)) return true;
     }
     return false;
 }
@@ -130,21 +141,35 @@ __device__ __forceinline__ bool tile_may_contribute(const CullRec& r, float cx, 
     const float xx = r.q0.x, xy = r.q0.y, yy = r.q0.z, bx = r.q0.w, by = r.q1.x, c0 = r.q1.y;
     const float x0 = __fadd_rn(gx0, -r.q2.x), x1 = __fadd_rn(gx1, -r.q2.x);
     const float y0 = __fadd_rn(gy0, -r.q2.y), y1 = __fadd_rn(gy1, -r.q2.y);
+    // rounding bounds, as in ellipse_hits_rect (explicit intrinsics: the two callers must agree bit for bit)
+    const float X = fmaxf(fabsf(x0), fabsf(x1)), Y = fmaxf(fabsf(y0), fabsf(y1));
+    const float axy = fabsf(xy), abx = fabsf(bx), aby = fabsf(by);
+    const float m0 = __fmaf_rn(xx, X, __fmul_rn(2.f, __fmaf_rn(axy, Y, abx)));
+    const float m1 = __fmaf_rn(yy, Y, __fmul_rn(2.f, aby));
+    const float E = __fmul_rn(QUADRIC_EPS, __fadd_rn(__fmaf_rn(m0, X, __fmul_rn(m1, Y)), fabsf(c0)));
     const float det = __fmaf_rn(xx, yy, -__fmul_rn(xy, xy));
     const float ex = __fmaf_rn(xy, by, -__fmul_rn(yy, bx)), ey = __fmaf_rn(xy, bx, -__fmul_rn(xx, by));
-    if (ex >= __fmul_rn(x0, det) && ex <= __fmul_rn(x1, det) && ey >= __fmul_rn(y0, det) && ey <= __fmul_rn(y1, det)) return true;
-    if (det_eval_rn(xx, xy, yy, bx, by, c0, x0, y0) <= 0.f || det_eval_rn(xx, xy, yy, bx, by, c0, x1, y0) <= 0.f ||
-        det_eval_rn(xx, xy, yy, bx, by, c0, x0, y1) <= 0.f || det_eval_rn(xx, xy, yy, bx, by, c0, x1, y1) <= 0.f) return true;
+    const float dm = __fmul_rn(QUADRIC_EPS, __fmaf_rn(xx, yy, __fmul_rn(xy, xy)));
+    const float tolx = __fmaf_rn(X, dm, __fmul_rn(QUADRIC_EPS, __fmaf_rn(axy, aby, __fmul_rn(yy, abx))));
+    const float toly = __fmaf_rn(Y, dm, __fmul_rn(QUADRIC_EPS, __fmaf_rn(axy, abx, __fmul_rn(xx, aby))));
+    if (ex >= __fadd_rn(__fmul_rn(x0, det), -tolx) && ex <= __fadd_rn(__fmul_rn(x1, det), tolx) &&
+        ey >= __fadd_rn(__fmul_rn(y0, det), -toly) && ey <= __fadd_rn(__fmul_rn(y1, det), toly)) return true;
+    if (det_eval_rn(xx, xy, yy, bx, by, c0, x0, y0) <= E || det_eval_rn(xx, xy, yy, bx, by, c0, x1, y0) <= E ||
+        det_eval_rn(xx, xy, yy, bx, by, c0, x0, y1) <= E || det_eval_rn(xx, xy, yy, bx, by, c0, x1, y1) <= E) return true;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const float yc = k ? y1 : y0;
         const float B = __fmaf_rn(xy, yc, bx);
         const float C = __fadd_rn(__fmul_rn(__fmaf_rn(yy, yc, __fmul_rn(2.f, by)), yc), c0);
-        if (-B > __fmul_rn(x0, xx) && -B < __fmul_rn(x1, xx) && __fmul_rn(C, xx) <= __fmul_rn(B, B)) return true;
+        const float BB = __fmul_rn(B, B);
+        if (-B > __fmul_rn(x0, xx) && -B < __fmul_rn(x1, xx) &&
+            __fmul_rn(C, xx) <= __fadd_rn(BB, __fmaf_rn(E, xx, __fmul_rn(QUADRIC_EPS, BB)))) return true;
         const float xc = k ? x1 : x0;
         const float B2 = __fmaf_rn(xy, xc, by);
         const float C2 = __fadd_rn(__fmul_rn(__fmaf_rn(xx, xc, __fmul_rn(2.f, bx)), xc), c0);
-        if (-B2 > __fmul_rn(y0, yy) && -B2 < __fmul_rn(y1, yy) && __fmul_rn(C2, yy) <= __fmul_rn(B2, B2)) return true;
+        const float BB2 = __fmul_rn(B2, B2);
+        if (-B2 > __fmul_rn(y0, yy) && -B2 < __fmul_rn(y1, yy) &&
+            __fmul_rn(C2, yy) <= __fadd_rn(BB2, __fmaf_rn(E, yy, __fmul_rn(QUADRIC_EPS, BB2)))) return true;
     }
     return false;
 }

@@ -40,12 +40,9 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-_LAST = {"num_rendered": 0}
-
-
 def last_num_rendered():
-    """num_rendered (R) of the most recent forward call in this process (bench statistics)."""
-    return _LAST["num_rendered"]
+    """True num_rendered (R) of this thread's most recent forward (the forward itself returns the binning layout size >= R)."""
+    return int(lib().gsr_last_num_rendered())
 
 
 def _check_inputs(means3D, scales):
@@ -93,7 +90,6 @@ class _RasterizeGaussians(torch.autograd.Function):
                     ptr(rot_c), ptr(cov_c), ptr(view), ptr(proj), ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
                     int(bool(rs.prefiltered)), ptr(color), ptr(radii), int(bool(rs.debug)), stream_ptr(dev)),
                     "gsr_gaussian_forward")
-        _LAST["num_rendered"] = num_rendered
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.dims = (P, M, H, W)

@@ -43,11 +43,9 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-_LAST = {"num_rendered": 0}
-
-
 def last_num_rendered():
-    return _LAST["num_rendered"]
+    """True num_rendered (R) of this thread's most recent forward (the forward itself returns the binning layout size >= R)."""
+    return int(lib().gsr_last_num_rendered())
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -94,7 +92,6 @@ class _RasterizeGaussians(torch.autograd.Function):
                     float(rs.tanfovy), int(bool(rs.prefiltered)), ptr(color), ptr(radii), ptr(out_observe),
                     ptr(out_all_map), ptr(out_plane_depth), int(geo), int(bool(rs.debug)), stream_ptr(dev)),
                     "gsr_plane_forward")
-        _LAST["num_rendered"] = num_rendered
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.dims = (P, M, H, W)

@@ -56,12 +56,11 @@ def _f32c(t, name, device):
     return t.contiguous()
 
 
-_LAST = {"num_rendered": 0}
-
-
 def last_num_rendered():
-    """num_rendered (R) of the most recent forward call in this process (bench statistics)."""
-    return _LAST["num_rendered"]
+    """True num_rendered (R) of this thread's most recent forward call (bench statistics).  The value the forward
+    returns -- and the autograd context carries to the backward -- is the binning layout size (>= R), see
+    include/gsr_b200.h "num_rendered WITHOUT a stream sync"."""
+    return int(lib().gsr_last_num_rendered())
 
 
 class _NullCtx:
@@ -129,7 +128,6 @@ class _RasterizeGaussians(torch.autograd.Function):
                     float(rs.tanfovx), float(rs.tanfovy), int(bool(rs.prefiltered)), ptr(color), ptr(others),
                     ptr(radii), int(bool(rs.debug)), _stream_ptr(dev)), "gsr_surfel_forward")
 
-        _LAST["num_rendered"] = num_rendered
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.dims = (P, M, H, W)

@@ -20,7 +20,7 @@
  *     (S/cuda_rasterizer/rasterizer.h:31-34, S/rasterize_points.cu:31-37).
  *     A callback must return a device pointer valid until the matching
  *     backward call has been enqueued (>= 256-byte aligned), or NULL on failure;
- *   - return value: >= 0 on success (forward: num_rendered), < 0 = GSR_E_*;
+ *   - return value: >= 0 on success (forward: binning layout size >= num_rendered), < 0 = GSR_E_*;
  *     gsr_last_error() returns a thread-local message.  No C++ exception
  *     crosses the boundary.
  */
@@ -77,8 +77,40 @@ int gsr_profile_read(float* ms_host);
 
 /* Runtime switches for validation.  "no_cull" = 1 disables the conservative
  * contribution boxes so every (pixel, splat) pair of a tile is evaluated like the
- * reference does; results must not change (tests/test_surfel_gpu.py). */
+ * reference does; results must not change (tests/test_surfel_gpu.py).
+ * "no_used_bits" = 1: the backward repeats the cull test instead of reading the forward's marks.
+ * "force_capacity" = n > 0: lay the binning buffer out for n entries regardless of history (exercises
+ * the re-run taken when num_rendered exceeds the predicted capacity); 0 restores the prediction. */
 int gsr_set_option(const char* name, int value);
+
+/* num_rendered WITHOUT a stream sync.  The reference blocks on a device->host copy of num_rendered in
+ * the middle of every forward to size its binning buffer (S/cuda_rasterizer/rasterizer_impl.cu:278-285).
+ * The *_forward entry points below instead lay the binning buffer out for a capacity predicted from
+ * earlier frames of the same (device, rasterizer, resolution), enqueue every kernel of the forward
+ * (lists clamped to the capacity), and then wait -- on a pinned host word the scan kernel writes, not on
+ * the stream -- for the true count: the GPU never idles, no cudaStreamSynchronize / cudaMemcpy is
+ * issued.  If the count exceeds the capacity (or there is no history yet) binning and rendering are
+ * enqueued again behind the clamped run with an exactly sized buffer; results are always exact.
+ * Consequence for callers: the forward's return value is the number of list entries the binning buffer
+ * was LAID OUT for (>= num_rendered).  It must be passed to the matching backward unchanged, which is
+ * all the reference wrapper does with it (S/diff_surfel_rasterization/__init__.py:97,121).  The true
+ * num_rendered of this host thread's most recent forward: */
+int gsr_last_num_rendered(void);
+
+/* Decision audit of a finished forward (verification only, no reference counterpart).  Re-walks the record stream
+ * kept in the forward's binning / image buffers with the render kernels' own arithmetic and writes, per pixel, the
+ * smallest relative distance of any blend decision to its threshold:
+ *   surfel  margins (5,H,W): alpha vs 1/255 | T(1-alpha) vs 1e-4 | T vs 0.5 | depth vs 0.2 | rho3d vs rho2d
+ *           (the tests of S/cuda_rasterizer/forward.cu:362-389,402)
+ *   ewa     margins (3,H,W): alpha vs 1/255 | T(1-alpha) vs 1e-4 | T vs 0.5   (G/forward.cu:336-356, L/forward.cu:381)
+ *   info (2,H,W) int: number of blended splats, Gaussian index of the last one (-1 = none)
+ *   mismatches (1 int, device): pixels whose replayed final_T / last contributor differ from the forward's (must be 0).
+ * Parity tests use it to accept a deviating pixel only when one of its decisions was marginal
+ * (tests/test_fullsize_parity_gpu.py).  P, R, width, height (and render_geo) as passed to / returned by the forward. */
+int gsr_surfel_audit(int P, int R, int width, int height, char* binning_buffer, char* image_buffer,
+                     float* margins, int* info, int* mismatches, void* stream);
+int gsr_ewa_audit(int P, int R, int width, int height, int render_geo, char* binning_buffer, char* image_buffer,
+                  float* margins, int* info, int* mismatches, void* stream);
 
 /* ---- 2DGS surfel rasterizer: diff_surfel_rasterization ------------------ */
 
@@ -88,7 +120,7 @@ int gsr_set_option(const char* name, int value);
  *   out_color (3,H,W), out_others (11,H,W), radii (P) are fully written.
  *   Exactly one of shs / colors_precomp and one of (scales+rotations) /
  *   transMat_precomp must be non-NULL.  scales is (P,2) packed.
- * Returns num_rendered. */
+ * Returns the binning layout size (>= num_rendered, see gsr_last_num_rendered). */
 int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer,
                        gsr_buffer_fn imageBuffer, void* user,
                        int P, int D, int M, const float* background, int width, int height,
@@ -132,7 +164,7 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,
  *   out_color (3,H,W) and radii (P) are fully written.  Exactly one of shs /
  *   colors_precomp and one of (scales+rotations) / cov3D_precomp must be non-NULL;
  *   scales is (P,3) packed, cov3D_precomp (P,6) upper-triangular.
- * Returns num_rendered. */
+ * Returns the binning layout size (>= num_rendered, see gsr_last_num_rendered). */
 int gsr_gaussian_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer,
                          gsr_buffer_fn imageBuffer, void* user,
                          int P, int D, int M, const float* background, int width, int height,

@@ -42,7 +42,9 @@ def _p(t):
 
 class RefSurfel:
     """Reference diff-surfel-rasterization forward/backward on raw device pointers.
-    Runs on the legacy default stream like the reference; callers synchronise."""
+    Runs on the legacy default stream like the reference (= torch's default current stream, so it is ordered after the
+    torch ops that produced its inputs; no synchronisation is added here); callers synchronise before reading results
+    on the host."""
 
     def __init__(self):
         self.L = _lib("surfel")
@@ -67,7 +69,6 @@ class RefSurfel:
                            tanfovx=tanfovx, tanfovy=tanfovy, means3D=means3D, shs=shs, colors=colors,
                            scales=scales, rotations=rotations, Tpre=transMat_precomp,
                            scale_modifier=scale_modifier, radii=radii, debug=debug)
-        torch.cuda.synchronize()
         rc = self.L.ref_forward(
             C.c_void_p(self.h), C.c_int(P), C.c_int(sh_degree), C.c_int(M), _p(bg), C.c_int(W), C.c_int(H),
             _p(means3D), _p(shs), _p(colors), _p(opacities), _p(scales), C.c_float(scale_modifier),
@@ -124,7 +125,6 @@ class RefGauss:
                            tanfovx=tanfovx, tanfovy=tanfovy, means3D=means3D, shs=shs, colors=colors,
                            scales=scales, rotations=rotations, cov3D=cov3D_precomp, all_map=all_map,
                            scale_modifier=scale_modifier, radii=radii, debug=debug, render_geo=render_geo)
-        torch.cuda.synchronize()
         head = [C.c_void_p(self.h), C.c_int(P), C.c_int(sh_degree), C.c_int(M), _p(bg), C.c_int(W), C.c_int(H),
                 _p(means3D), _p(shs), _p(colors), _p(opacities), _p(scales), C.c_float(scale_modifier),
                 _p(rotations), _p(cov3D_precomp)]

@@ -28,9 +28,17 @@ def to_torch(scene, device="cuda"):
                 bg=t(cam.bg), view=t(cam.viewmatrix), proj=t(cam.projmatrix), campos=t(cam.campos))
 
 
+def _audit(out_tensor, out):
+    """Decision margins of the forward that produced `out_tensor` (gsr_b200.audit); must run before the backward."""
+    from gsr_b200.audit import decision_margins
+    margins, info, mism = decision_margins(out_tensor)
+    out["margins"], out["audit_info"], out["audit_mismatches"] = margins.cpu().numpy(), info.cpu().numpy(), mism
+
+
 def run_product_surfel(scene, g_color=None, g_others=None, device="cuda", transMat_precomp=None,
-                       scale_modifier=1.0, tt=None):
-    """Forward (+ backward when upstream grads are given) through the drop-in Python API."""
+                       scale_modifier=1.0, tt=None, audit=False, strided_scales=False):
+    """Forward (+ backward when upstream grads are given) through the drop-in Python API.
+    strided_scales: hand `scales` over as the stride-3 view scaling[:, :2] GS-SR uses (scaffold_2dgs_scene.py:17)."""
     import torch
     from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     cam = scene.cam
@@ -48,12 +56,19 @@ def run_product_surfel(scene, g_color=None, g_others=None, device="cuda", transM
         scale_modifier=scale_modifier, viewmatrix=tt["view"], projmatrix=tt["proj"], sh_degree=scene.sh_degree,
         campos=tt["campos"], prefiltered=False, debug=False)
     rast = GaussianRasterizer(rs)
+    scales_arg = leaves.get("scales")
+    if strided_scales and scales_arg is not None:
+        s3 = torch.cat([tt["scales"], torch.ones_like(tt["scales"][:, :1])], dim=1).requires_grad_(True)
+        leaves["scales"] = s3
+        scales_arg = s3[:, :2]
     color, radii, others = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
                                 shs=leaves.get("shs"), colors_precomp=leaves.get("colors"),
-                                scales=leaves.get("scales"), rotations=leaves.get("rotations"),
+                                scales=scales_arg, rotations=leaves.get("rotations"),
                                 cov3D_precomp=leaves.get("transMat"))
     out = dict(color=color.detach().cpu().numpy(), others=others.detach().cpu().numpy(),
                radii=radii.cpu().numpy())
+    if audit:
+        _audit(color, out)
     if g_color is not None:
         gc = torch.from_numpy(g_color).to(device)
         go = torch.from_numpy(g_others).to(device)
@@ -175,7 +190,7 @@ def _np(t):
 
 
 def run_product_gauss(scene, g_color=None, plane=False, all_map=None, g_all_map=None, g_plane_depth=None,
-                      cov3D_precomp=None, scale_modifier=1.0, render_geo=True, device="cuda", tt=None):
+                      cov3D_precomp=None, scale_modifier=1.0, render_geo=True, device="cuda", tt=None, audit=False):
     """Forward (+ backward) through the drop-in diff_gaussian_rasterization / diff_plane_rasterization API."""
     import torch
     if plane:
@@ -212,6 +227,8 @@ def run_product_gauss(scene, g_color=None, plane=False, all_map=None, g_all_map=
     else:
         color, radii = rast(**common)
         out = dict(color=_np(color), radii=_np(radii))
+    if audit:
+        _audit(color, out)
     if g_color is not None:
         outs, gs = [color], [torch.from_numpy(g_color).to(device)]
         if plane and render_geo and g_all_map is not None:

@@ -141,6 +141,32 @@ def test_ewa_culling_never_changes_results():
         assert np.allclose(a["grads"][k], b["grads"][k], rtol=1e-4, atol=1e-9), k
 
 
+@pytest.mark.parametrize("plane", [False, True])
+@pytest.mark.parametrize("cap", [500, 30_000_000])
+def test_ewa_binning_capacity_prediction_paths(plane, cap):
+    """No stream sync for num_rendered (include/gsr_b200.h): a forced capacity far below R takes the clamped run + exact
+    re-run (out_observe, accumulated with atomics, must start from zero again), one far above R lets the speculative run
+    stand; results are bit-identical to the default path."""
+    import gsr_b200
+    sc = synth.make_scene(40000, 320, 240, seed=61, rotate_camera=True, scale_dims=3)
+    gc, _ = synth.make_upstream_grads(320, 240, seed=62)
+    kw = dict(g_color=gc, plane=plane)
+    if plane:
+        kw.update(all_map=synth.make_all_map(sc), render_geo=True, g_all_map=np.zeros((5, 240, 320), np.float32),
+                  g_plane_depth=np.zeros((1, 240, 320), np.float32))
+    base = hz.run_product_gauss(sc, **kw)
+    L = gsr_b200.lib()
+    L.gsr_set_option(b"force_capacity", cap)
+    try:
+        forced = hz.run_product_gauss(sc, **kw)
+    finally:
+        L.gsr_set_option(b"force_capacity", 0)
+    for k in ("color", "radii") + (("out_all_map", "plane_depth", "observe") if plane else ()):
+        assert np.array_equal(base[k], forced[k]), k
+    for k in ("opacities", "colors", "means3D"):
+        assert hz.rel_linf(forced["grads"][k], base["grads"][k]) <= 2e-5, k
+
+
 def test_ewa_edge_cases_empty_culled_and_strided():
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     sc = synth.make_scene(64, 48, 32, seed=61, scale_dims=3, bg=(0.2, 0.4, 0.6))

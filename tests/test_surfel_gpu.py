@@ -224,6 +224,36 @@ def test_culling_never_changes_results():
         assert hz.rel_linf(cul["grads"][k], full["grads"][k]) <= 2e-5, k  # atomic order only
 
 
+@pytest.mark.parametrize("cap", [1000, 40_000_000])
+def test_binning_capacity_prediction_paths(cap):
+    """The forward lays the binning buffer out BEFORE it knows num_rendered (no stream sync, include/gsr_b200.h).  Forced
+    capacities exercise both outcomes: far too small -> the clamped run is followed by an exact re-run; larger than needed ->
+    the speculative run stands.  Either way images are bit-identical to the default path and the backward works on the
+    layout the forward reports."""
+    import gsr_b200
+    from diff_surfel_rasterization import last_num_rendered
+    sc = synth.make_scene(60000, 400, 300, seed=71, rotate_camera=True)
+    gc, go = synth.make_upstream_grads(400, 300, seed=72)
+    tt = hz.to_torch(sc)
+    base = hz.run_product_surfel(sc, gc, go, tt=tt)          # first call of this resolution: waits for R, exact layout
+    R = last_num_rendered()
+    assert 1000 < R < 40_000_000
+    again = hz.run_product_surfel(sc, gc, go, tt=tt)         # second call: capacity predicted from the first
+    assert last_num_rendered() == R
+    L = gsr_b200.lib()
+    L.gsr_set_option(b"force_capacity", cap)
+    try:
+        forced = hz.run_product_surfel(sc, gc, go, tt=tt)
+        assert last_num_rendered() == R
+    finally:
+        L.gsr_set_option(b"force_capacity", 0)
+    for other in (again, forced):
+        assert np.array_equal(other["color"], base["color"]) and np.array_equal(other["others"], base["others"])
+        assert np.array_equal(other["radii"], base["radii"])
+        for k in ("means3D", "colors", "opacities", "scales", "rotations", "means2D"):
+            assert hz.rel_linf(other["grads"][k], base["grads"][k]) <= 2e-5, k  # atomic order only
+
+
 def test_empty_all_culled_and_background():
     sc = synth.make_scene(64, 48, 32, seed=3, bg=(0.25, 0.5, 0.75))
     gc, go = synth.make_upstream_grads(48, 32)
