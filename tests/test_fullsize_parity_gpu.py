@@ -28,8 +28,8 @@ import synth
 pytestmark = pytest.mark.gpu
 
 FWD_TOL, GRAD_TOL = 1e-4, 1e-3
-DIST_TOL = 5e-3            # distortion channel: difference of O(1) blended moments, channel max ~1e-3 (see below)
-BAND = 1e-3                # a decision within this relative distance of its threshold may flip between implementations
+DIST_TOL = 2e-3            # distortion channel: difference of O(1) blended moments, channel max ~1e-3 (measured 4.2e-4 at cfg-B)
+BAND = 2e-4                # a decision within this relative distance of its threshold may flip between implementations (measured <= 5.8e-5)
 EDGE_COS = 1e-2
 MAX_EXCUSED = 1e-4
 
