@@ -57,6 +57,8 @@ cudaError_t launch_surfel_audit(int, const uint32_t*, const float4*, size_t, int
                                 float*, int*, int*, cudaStream_t);
 cudaError_t launch_ewa_audit(int, const uint32_t*, const float4*, size_t, int, int, int, const float*, const uint32_t*, uint32_t,
                              float*, int*, int*, cudaStream_t);
+cudaError_t launch_depth_normal_fwd(int, int, const float*, const float*, const float*, float*, cudaStream_t);
+cudaError_t launch_depth_normal_bwd(int, int, const float*, const float*, const float*, const float*, float*, float*, cudaStream_t);
 // ---- error string -------------------------------------------------------------
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -872,6 +874,22 @@ int gsr_ewa_audit(int P, int R, int width, int height, int render_geo, char* bin
     GSR_CUDA_CHECK(cudaMemsetAsync(mismatches, 0, sizeof(int), s));
     GSR_CUDA_CHECK(launch_ewa_audit(vc.gx * vc.gy, iw.tile_offset, bw.planes, bw.plane_stride, width, height, vc.gx, iw.final_T,
                                     iw.n_contrib, idx_mask, margins, info, mismatches, s));
+    return GSR_OK;
+}
+
+int gsr_depth_normal_forward(int H, int W, const float* depth, const float* kinv, const float* weight, float* normal,
+                             void* stream) {
+    if (H <= 0 || W <= 0 || !depth || !kinv || !normal) { set_error("gsr_depth_normal_forward: invalid argument"); return GSR_E_INVALID; }
+    GSR_CUDA_CHECK(launch_depth_normal_fwd(H, W, depth, kinv, weight, normal, (cudaStream_t)stream));
+    return GSR_OK;
+}
+
+int gsr_depth_normal_backward(int H, int W, const float* depth, const float* kinv, const float* weight,
+                              const float* dL_dnormal, float* scratch, float* dL_ddepth, void* stream) {
+    if (H <= 0 || W <= 0 || !depth || !kinv || !dL_dnormal || !scratch || !dL_ddepth) {
+        set_error("gsr_depth_normal_backward: invalid argument"); return GSR_E_INVALID;
+    }
+    GSR_CUDA_CHECK(launch_depth_normal_bwd(H, W, depth, kinv, weight, dL_dnormal, scratch, dL_ddepth, (cudaStream_t)stream));
     return GSR_OK;
 }
 

@@ -76,6 +76,11 @@ def lib():
     L.gsr_surfel_post_forward.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float, _fp, _fp, _fp, C.c_void_p]
     L.gsr_surfel_post_backward.restype = C.c_int
     L.gsr_surfel_post_backward.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float] + [_fp] * 6 + [C.c_void_p]
+    if hasattr(L, "gsr_depth_normal_forward"):
+        L.gsr_depth_normal_forward.restype = C.c_int
+        L.gsr_depth_normal_forward.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]
+        L.gsr_depth_normal_backward.restype = C.c_int
+        L.gsr_depth_normal_backward.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]
     if hasattr(L, "gsr_surfel_audit"):      # absent only from older builds loaded through the GSR_B200_LIB developer hook
         L.gsr_last_num_rendered.restype = C.c_int
         L.gsr_last_num_rendered.argtypes = []

@@ -317,6 +317,19 @@ int gsr_surfel_post_backward(int height, int width, const float* allmap, const f
                              const float* surf_depth, const float* g_render_normal, const float* g_surf_depth,
                              const float* g_surf_normal, float* scratch6, float* dL_dallmap, void* stream);
 
+/* ---- PGSR depth -> normal -------------------------------------------------------
+ * Replaces normal_from_depth_image(depth, intrinsic, extrinsic, offset=None)
+ * (gssr/utils/graphics_utils.py:139-146 -> depth2point_cam :88-99, depth_pcd2normal :110-137) as called by
+ * PGSRScene.render_normal (gssr/scene/pgsr_scene.py:227-238,320).
+ *   depth (H,W) device; kinv: the 9 floats of inverse(K^T), row-major, on the DEVICE (the caller takes the inverse
+ *   with the reference's own float32 torch op; no host read-back); weight (H,W) device or NULL: per-pixel factor fused into the output
+ *   (PGSR multiplies by the detached alpha); normal (3,H,W) fully written, zero on the one-pixel border.
+ * Backward: dL_dnormal (3,H,W) -> dL_ddepth (H,W) fully written; scratch = 6*H*W floats. */
+int gsr_depth_normal_forward(int H, int W, const float* depth, const float* kinv, const float* weight,
+                             float* normal, void* stream);
+int gsr_depth_normal_backward(int H, int W, const float* depth, const float* kinv, const float* weight,
+                              const float* dL_dnormal, float* scratch, float* dL_ddepth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,25 @@ def test_pgsr_iteration_matches_reference_kernels():
     assert abs(la - lb) <= 2e-3 * abs(lb), (la, lb)
 
 
+def test_fused_depth_normal_in_the_pgsr_iteration():
+    """Swapping the torch normal_from_depth_image chain x alpha for gsr_b200.depth_normal leaves the PGSR iteration's losses
+    and densification statistics unchanged (the normal loss is the only consumer, pgsr_scene.py:105-113)."""
+    from train_harness import MiniPGSRTrainer
+    kw = dict(P=20000, W=256, H=144, seed=13, impl="ours")
+    a, b = MiniPGSRTrainer(**kw), MiniPGSRTrainer(**kw)
+    a.fused_post = True
+    la, da = a.step()
+    lb, db = b.step()
+    for k in da:
+        assert abs(da[k] - db[k]) <= 2e-5 * max(abs(db[k]), 1e-3), (k, da[k], db[k])
+    for x, y in ((a.xyz_gradient_accum, b.xyz_gradient_accum), (a.xyz_gradient_accum_abs, b.xyz_gradient_accum_abs)):
+        assert float((x.double() - y.double()).norm() / y.double().norm()) <= 1e-3
+    for _ in range(2):
+        la, _ = a.step()
+        lb, _ = b.step()
+    assert abs(la - lb) <= 2e-3 * abs(lb), (la, lb)
+
+
 def test_fused_ssim_in_the_training_iteration():
     """Swapping VanillaScene.ssim for gsr_b200.ssim leaves the iteration's losses and statistics unchanged."""
     from train_harness import MiniTwoDGSTrainer

@@ -419,7 +419,13 @@ class MiniPGSRTrainer(MiniTwoDGSTrainer):
             image, radii, observe, out_all_map, plane_depth = _RefPlaneFn.apply(means3D, sp, sp_abs, colors, opacity, scales,
                                                                                 rotations, all_map, self.refs[vi], rs)
         rendered_normal, rendered_alpha = out_all_map[0:3], out_all_map[3:4]
-        depth_normal = self.normal_from_depth(plane_depth.squeeze(), cam) * rendered_alpha.detach()
+        if getattr(self, "fused_post", False):      # fused depth -> normal x alpha (gsr_b200.depth_normal, csrc/depth_normal.cu)
+            from gsr_b200.depth_normal import render_normal_weighted
+            fx, fy = self.W / (2 * cam["tanfovx"]), self.H / (2 * cam["tanfovy"])
+            K = torch.tensor([[fx, 0, self.W / 2], [0, fy, self.H / 2], [0, 0, 1]], dtype=torch.float32)   # get_calib_matrix_nerf
+            depth_normal = render_normal_weighted(plane_depth.squeeze(), K, rendered_alpha.squeeze(0))
+        else:
+            depth_normal = self.normal_from_depth(plane_depth.squeeze(), cam) * rendered_alpha.detach()
         return dict(render=image, viewspace_points=sp, viewspace_points_abs=sp_abs, visibility_filter=radii > 0, radii=radii,
                     out_observe=observe, rendered_normal=rendered_normal, plane_depth=plane_depth,
                     rendered_distance=out_all_map[4:5], depth_normal=depth_normal)
