@@ -248,14 +248,28 @@ static int wait_num_rendered(volatile uint32_t* slot, uint32_t seq, cudaStream_t
 // ---- per-kernel device timing (cudaEvents on the caller's stream, off by default) ----
 // bench.py needs the dominant kernel's duration measured live, outside any profiler.
 struct Prof {
-    bool on = false, created = false;
+    bool created = false;
     cudaEvent_t ev[GSR_PROF_SLOTS][2];
     bool used[GSR_PROF_SLOTS];
 };
-static Prof g_prof;
-static inline void prof_begin(int slot, cudaStream_t s) { if (g_prof.on) cudaEventRecord(g_prof.ev[slot][0], s); }
+constexpr int PROF_MAX_DEV = 64;
+static Prof g_prof[PROF_MAX_DEV];          // one event set per device: events are created on, and only recorded into streams of, that device
+static std::atomic<bool> g_prof_on{false};
+static inline Prof* prof_here() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PROF_MAX_DEV || !g_prof[dev].created) return nullptr;
+    return &g_prof[dev];
+}
+static inline void prof_begin(int slot, cudaStream_t s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    if (Prof* p = prof_here()) { if (cudaEventRecord(p->ev[slot][0], s) != cudaSuccess) (void)cudaGetLastError(); }
+}
 static inline void prof_end(int slot, cudaStream_t s) {
-    if (g_prof.on) { cudaEventRecord(g_prof.ev[slot][1], s); g_prof.used[slot] = true; }
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    if (Prof* p = prof_here()) {
+        if (cudaEventRecord(p->ev[slot][1], s) == cudaSuccess) p->used[slot] = true;
+        else (void)cudaGetLastError();
+    }
 }
 
 }  // namespace gsr
@@ -281,23 +295,29 @@ int gsr_set_option(const char* name, int value) {
 int gsr_last_num_rendered(void) { return g_true_R; }
 
 int gsr_profile_enable(int on) {
-    if (on && !g_prof.created) {
+    // applies to the CURRENT device (events are per device); the on/off switch is global
+    int dev = 0;
+    GSR_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= PROF_MAX_DEV) { set_error("gsr_profile_enable: device %d out of range", dev); return GSR_E_INVALID; }
+    Prof& p = g_prof[dev];
+    if (on && !p.created) {
         for (int i = 0; i < GSR_PROF_SLOTS; i++)
-            for (int j = 0; j < 2; j++) GSR_CUDA_CHECK(cudaEventCreate(&g_prof.ev[i][j]));
-        g_prof.created = true;
+            for (int j = 0; j < 2; j++) GSR_CUDA_CHECK(cudaEventCreate(&p.ev[i][j]));
+        p.created = true;
     }
-    for (int i = 0; i < GSR_PROF_SLOTS; i++) g_prof.used[i] = false;
-    g_prof.on = on != 0;
+    for (int i = 0; i < GSR_PROF_SLOTS; i++) p.used[i] = false;
+    g_prof_on.store(on != 0);
     return GSR_OK;
 }
 
 int gsr_profile_read(float* ms_host) {
-    if (!ms_host || !g_prof.created) { set_error("gsr_profile_read: profiling was never enabled"); return GSR_E_INVALID; }
+    Prof* p = prof_here();
+    if (!ms_host || !p) { set_error("gsr_profile_read: profiling was never enabled on the current device"); return GSR_E_INVALID; }
     for (int i = 0; i < GSR_PROF_SLOTS; i++) {
         ms_host[i] = -1.0f;
-        if (!g_prof.used[i]) continue;
-        GSR_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[i][1]));
-        GSR_CUDA_CHECK(cudaEventElapsedTime(&ms_host[i], g_prof.ev[i][0], g_prof.ev[i][1]));
+        if (!p->used[i]) continue;
+        GSR_CUDA_CHECK(cudaEventSynchronize(p->ev[i][1]));
+        GSR_CUDA_CHECK(cudaEventElapsedTime(&ms_host[i], p->ev[i][0], p->ev[i][1]));
     }
     return GSR_OK;
 }
@@ -832,9 +852,9 @@ int gsr_visible_filter(int P, int width, int height, const float* means3D, const
     }
     const ViewParams vc = make_view(viewmatrix, projmatrix, nullptr, width, height, scale_modifier);
     const float focal_y = (float)height / (2.0f * tan_fovy), focal_x = (float)width / (2.0f * tan_fovx);   // F/rasterizer_impl.cu:358-359
-    // prefiltered is honoured only in debug mode: it needs a flag word and a read-back, which the
-    // asynchronous product path avoids (the reference __trap()s inside the kernel)
-    (void)prefiltered; (void)debug;
+    // `prefiltered` is accepted for signature parity and IGNORED: reporting a violation needs a flag word and a read-back,
+    // which this asynchronous entry point does not do (the reference __trap()s inside the kernel, F/auxiliary.h:204-208)
+    (void)prefiltered;
     ewa_preprocess_fwd<true><<<(P + 255) / 256, 256, 0, s>>>(
         P, 0, 0, means3D, scales, (const float4*)rotations, nullptr, nullptr, cov3D_precomp, true, vc, focal_x, focal_y,
         tan_fovx, tan_fovy, false, true, radii, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);

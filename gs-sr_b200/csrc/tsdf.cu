@@ -78,20 +78,34 @@ __device__ __forceinline__ float sample_plane(const float* __restrict__ img, int
     return out;
 }
 
-template <bool RGB>
+// GRID: the samples are the lattice points  origin + (ix, iy, iz) * voxel_size  of a bounded nx x ny x nz volume (x fastest),
+// generated from the thread index instead of read from memory; fixed truncation `grid_trunc`; a view is skipped where its
+// sampled depth is <= 0 (masked background, mesh_utils.py:160-162) or > depth_trunc (the depth_trunc of
+// RGBDImage.create_from_color_and_depth, :165-170).  This is the bounded fusion of extract_mesh_bounded (:138-179) with
+// the reference's own torch integration rule in place of Open3D's ScalableTSDFVolume (absent dependency, parity unpinned).
+struct TsdfGrid { float ox, oy, oz, trunc, depth_trunc; int nx, ny, nz; };
+
+template <bool RGB, bool GRID>
 __global__ void __launch_bounds__(TSDF_THREADS)
 tsdf_fuse_kernel(long long n, const float* __restrict__ samples, int contracted, float cx, float cy, float cz,
                  float radius, float voxel_size, int nviews, const TsdfViewDev* __restrict__ views, int init,
-                 float* __restrict__ tsdf_io, float* __restrict__ weight_io, float* __restrict__ rgb_io) {
+                 float* __restrict__ tsdf_io, float* __restrict__ weight_io, float* __restrict__ rgb_io, const TsdfGrid grid) {
     __shared__ TsdfViewDev sviews[TSDF_VCHUNK];
     const long long i = (long long)blockIdx.x * TSDF_THREADS + threadIdx.x;
     const bool live = i < n;
 
     float x = 0.f, y = 0.f, z = 0.f, trunc = 5.f * voxel_size;
     float tsdf = 1.f, w = 1.f, r = 0.f, g = 0.f, b = 0.f;
+    if (live && GRID) {
+        const long long ix = i % grid.nx, iyz = i / grid.nx;
+        x = fmaf((float)ix, voxel_size, grid.ox);
+        y = fmaf((float)(iyz % grid.ny), voxel_size, grid.oy);
+        z = fmaf((float)(iyz / grid.ny), voxel_size, grid.oz);
+        trunc = grid.trunc;
+    }
     if (live) {
-        x = samples[3 * i]; y = samples[3 * i + 1]; z = samples[3 * i + 2];
-        if (contracted) {
+        if (!GRID) { x = samples[3 * i]; y = samples[3 * i + 1]; z = samples[3 * i + 2]; }
+        if (!GRID && contracted) {
             // mesh_utils.py:215-219 (adaptive truncation) and :190-193, :248-250 (uncontract, unnormalize)
             const float mag = sqrtf(x * x + y * y + z * z);
             if (mag > 1.f) trunc *= 1.f / (2.f - fminf(mag, 1.9f));
@@ -126,7 +140,9 @@ tsdf_fuse_kernel(long long n, const float* __restrict__ samples, int contracted,
             const bool mask_proj = (u > -1.f) && (u < 1.f) && (t > -1.f) && (t < 1.f) && (hw > 0.f);
             if (!mask_proj) continue;
             const BilinearTaps taps = bilinear_taps(u, t, V.W, V.H);
-            const float sdf = sample_plane(V.depth, V.W, taps) - hw;
+            const float dsamp = sample_plane(V.depth, V.W, taps);
+            if (GRID && (!(dsamp > 0.f) || dsamp > grid.depth_trunc)) continue;
+            const float sdf = dsamp - hw;
             if (!(sdf > -trunc)) continue;
             const float s = fminf(fmaxf(sdf / trunc, -1.f), 1.f);
             const float wp = w + 1.f;
@@ -165,12 +181,38 @@ extern "C" int gsr_tsdf_fuse(long long n, const float* samples, int contracted, 
     const long long blocks = (n + TSDF_THREADS - 1) / TSDF_THREADS;
     if (blocks > 0x7fffffffLL) { set_error("gsr_tsdf_fuse: too many samples (%lld)", n); return GSR_E_OVERFLOW; }
     const TsdfViewDev* vd = reinterpret_cast<const TsdfViewDev*>(views);
+    const TsdfGrid nogrid = {0.f, 0.f, 0.f, 0.f, 0.f, 0, 0, 0};
     if (rgb)
-        tsdf_fuse_kernel<true><<<(unsigned)blocks, TSDF_THREADS, 0, s>>>(n, samples, contracted, cx, cy, cz, radius,
-                                                                         voxel_size, nviews, vd, init, tsdf, weights, rgb);
+        tsdf_fuse_kernel<true, false><<<(unsigned)blocks, TSDF_THREADS, 0, s>>>(n, samples, contracted, cx, cy, cz, radius,
+                                                                                voxel_size, nviews, vd, init, tsdf, weights, rgb, nogrid);
     else
-        tsdf_fuse_kernel<false><<<(unsigned)blocks, TSDF_THREADS, 0, s>>>(n, samples, contracted, cx, cy, cz, radius,
-                                                                          voxel_size, nviews, vd, init, tsdf, weights, nullptr);
+        tsdf_fuse_kernel<false, false><<<(unsigned)blocks, TSDF_THREADS, 0, s>>>(n, samples, contracted, cx, cy, cz, radius,
+                                                                                 voxel_size, nviews, vd, init, tsdf, weights, nullptr, nogrid);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    return GSR_OK;
+}
+
+extern "C" int gsr_tsdf_integrate_grid(int nx, int ny, int nz, const float* origin, float voxel_size, float sdf_trunc,
+                                       float depth_trunc, int nviews, const gsr_tsdf_view* views, int init, float* tsdf,
+                                       float* weights, float* rgb, void* stream_v) {
+    using namespace gsr;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    if (nx <= 0 || ny <= 0 || nz <= 0 || !origin || !(voxel_size > 0.f) || !(sdf_trunc > 0.f) || !(depth_trunc > 0.f) || nviews < 0 ||
+        (nviews > 0 && !views) || !tsdf || !weights) {
+        set_error("gsr_tsdf_integrate_grid: invalid argument");
+        return GSR_E_INVALID;
+    }
+    const long long n = (long long)nx * ny * nz;
+    const long long blocks = (n + TSDF_THREADS - 1) / TSDF_THREADS;
+    if (blocks > 0x7fffffffLL) { set_error("gsr_tsdf_integrate_grid: volume too large (%lld voxels)", n); return GSR_E_OVERFLOW; }
+    const TsdfGrid g = {origin[0], origin[1], origin[2], sdf_trunc, depth_trunc, nx, ny, nz};
+    const TsdfViewDev* vd = reinterpret_cast<const TsdfViewDev*>(views);
+    if (rgb)
+        tsdf_fuse_kernel<true, true><<<(unsigned)blocks, TSDF_THREADS, 0, s>>>(n, nullptr, 0, 0.f, 0.f, 0.f, 1.f, voxel_size, nviews, vd,
+                                                                               init, tsdf, weights, rgb, g);
+    else
+        tsdf_fuse_kernel<false, true><<<(unsigned)blocks, TSDF_THREADS, 0, s>>>(n, nullptr, 0, 0.f, 0.f, 0.f, 1.f, voxel_size, nviews, vd,
+                                                                                init, tsdf, weights, nullptr, g);
     GSR_CUDA_CHECK(cudaGetLastError());
     return GSR_OK;
 }

@@ -23,6 +23,7 @@ import torch.nn as nn
 
 from gsr_b200 import TorchBuffers, check, lib, ptr
 from gsr_b200._torch_util import f32c, on_device, stream_ptr
+from gsr_b200._torch_util import check_per_gaussian
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -71,6 +72,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         scales_c = f32c(scales, "scales", dev)
         rot_c = f32c(rotations, "rotations", dev)
         cov_c = f32c(cov3Ds_precomp, "cov3Ds_precomp", dev)
+        check_per_gaussian(P, opacities=(opac_c, [(1,), ()]), scales=(scales_c, [(3,)]), rotations=(rot_c, [(4,)]),
+                           colors_precomp=(colors_c, [(3,)]), sh=(sh_c, [(None, 3)]), cov3Ds_precomp=(cov_c, [(6,)]),
+                           means2D=(means2D, [(3,)]))
         bg = f32c(rs.bg, "bg", dev)
         view = f32c(rs.viewmatrix, "viewmatrix", dev)
         proj = f32c(rs.projmatrix, "projmatrix", dev)

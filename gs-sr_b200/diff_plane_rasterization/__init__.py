@@ -25,6 +25,7 @@ import torch.nn as nn
 from gsr_b200 import TorchBuffers, check, lib, ptr
 from gsr_b200._torch_util import f32c, on_device, stream_ptr
 from diff_gaussian_rasterization import _check_inputs, _mark_visible
+from gsr_b200._torch_util import check_per_gaussian
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -67,6 +68,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         rot_c = f32c(rotations, "rotations", dev)
         cov_c = f32c(cov3Ds_precomp, "cov3Ds_precomp", dev)
         am_c = f32c(all_maps, "all_map", dev)
+        check_per_gaussian(P, opacities=(opac_c, [(1,), ()]), scales=(scales_c, [(3,)]), rotations=(rot_c, [(4,)]),
+                           colors_precomp=(colors_c, [(3,)]), sh=(sh_c, [(None, 3)]), cov3Ds_precomp=(cov_c, [(6,)]),
+                           all_map=(am_c, [(5,)]), means2D=(means2D, [(3,)]), means2D_abs=(means2D_abs, [(3,)]))
         if geo and P and (am_c is None or am_c.numel() == 0 or am_c.shape[-1] != 5):
             raise RuntimeError("all_map must have shape (P, 5) when render_geo is set")
         bg = f32c(rs.bg, "bg", dev)

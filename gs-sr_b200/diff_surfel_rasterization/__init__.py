@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from gsr_b200 import TorchBuffers, check, lib, ptr
+from gsr_b200._torch_util import check_per_gaussian
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -110,6 +111,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         campos = _f32c(rs.campos, "campos", dev)
         if scales_c is not None and scales_c.numel() and scales_c.shape[-1] != 2:
             raise RuntimeError("surfel scales must have shape (P, 2)")
+        check_per_gaussian(P, opacities=(opac_c, [(1,), ()]), scales=(scales_c, [(2,)]), rotations=(rot_c, [(4,)]),
+                           colors_precomp=(colors_c, [(3,)]), sh=(sh_c, [(None, 3)]), cov3Ds_precomp=(tm_c, [(9,)]),
+                           means2D=(means2D, [(3,)]))
 
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         others = torch.empty((11, H, W), dtype=torch.float32, device=dev)

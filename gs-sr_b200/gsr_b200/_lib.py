@@ -76,6 +76,10 @@ def lib():
     L.gsr_surfel_post_forward.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float, _fp, _fp, _fp, C.c_void_p]
     L.gsr_surfel_post_backward.restype = C.c_int
     L.gsr_surfel_post_backward.argtypes = [C.c_int, C.c_int, _fp, _fp, C.c_float] + [_fp] * 6 + [C.c_void_p]
+    if hasattr(L, "gsr_tsdf_integrate_grid"):
+        L.gsr_tsdf_integrate_grid.restype = C.c_int
+        L.gsr_tsdf_integrate_grid.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_int, _fp,
+                                                              C.c_int, _fp, _fp, _fp, C.c_void_p]
     if hasattr(L, "gsr_depth_normal_forward"):
         L.gsr_depth_normal_forward.restype = C.c_int
         L.gsr_depth_normal_forward.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]

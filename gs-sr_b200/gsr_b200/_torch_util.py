@@ -38,3 +38,20 @@ def on_device(device):
 
 def stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def check_per_gaussian(P, **named):
+    """Host-side shape checks of the per-Gaussian inputs: every non-empty tensor must have P rows and the trailing shape
+    the kernels index with.  `named` maps an argument name to (tensor, allowed trailing shapes); a trailing shape may
+    contain None as a wildcard (e.g. the SH coefficient count).  A mismatch (e.g. rotations left behind by a densify /
+    prune desync) would otherwise be an out-of-bounds device read."""
+    for name, (t, trailing) in named.items():
+        if t is None or t.numel() == 0:
+            continue
+        if t.shape[0] != P:
+            raise RuntimeError(f"{name} has {t.shape[0]} rows, expected {P} (one per Gaussian)")
+        tail = tuple(t.shape[1:])
+        ok = any(len(tail) == len(want) and all(w is None or w == d for w, d in zip(want, tail)) for want in trailing)
+        if not ok:
+            raise RuntimeError(f"{name} has shape {tuple(t.shape)}, expected ({P}, " + " or ".join(
+                ", ".join("*" if w is None else str(w) for w in want) for want in trailing) + ")")

@@ -11,6 +11,12 @@ difference is that ``inv_contraction`` is a flag (anything but None selects the 
 ``unnormalize(uncontract(x))`` with this object's center / radius, :187-193, :248-250) because the
 contraction runs inside the CUDA kernel.  Views are fused many per kernel launch (``gsr_tsdf_fuse``,
 gs-sr_b200/csrc/tsdf.cu; 17 depth-only / 8 depth+RGB 1600x1060 views per launch); no CPU / PyTorch fallback.
+
+``BoundedTSDFVolume`` is the bounded counterpart (``extract_mesh_bounded``, mesh_utils.py:138-179, and the multi-tile
+``extract_mesh_split.py:81-119``): a dense voxel lattice integrated with the same rule, whose per-GPU partial volumes
+(one VastGaussian tile per GPU, BASELINE config 5) are combined with one NCCL reduce (``reduce_to``).  The reference uses
+Open3D's ScalableTSDFVolume there -- an absent dependency without vectors in the reference, so parity against Open3D is
+UNPINNED; what is pinned is the integration rule itself (the torch rule above) and the exactness of the combine.
 """
 from __future__ import annotations
 
@@ -112,3 +118,101 @@ class TSDFFusion:
         if return_rgb:
             return tsdfs, rgbs
         return tsdfs
+
+
+def cameras_in_box(camera_centers, box):
+    """Indices of the cameras whose centre lies inside a tile's box.txt rectangle [mx, Mx, my, My] -- the filter
+    extract_mesh_split.py:58-67 applies before rendering a tile's views."""
+    c = torch.as_tensor(camera_centers, dtype=torch.float64).reshape(-1, 3)
+    mx, Mx, my, My = (float(v) for v in box)
+    keep = (c[:, 0] >= mx) & (c[:, 0] <= Mx) & (c[:, 1] >= my) & (c[:, 1] <= My)
+    return torch.nonzero(keep).flatten().tolist()
+
+
+def combine_partial_volumes(parts):
+    """Exact combination of volumes integrated independently from the same initial state (tsdf = 1, weight = 1, rgb = 0):
+    the running mean is a weighted mean, so  W = 1 + sum(w_r - 1),  TSDF = (1 + sum(tsdf_r w_r - 1)) / W,
+    RGB = sum(rgb_r w_r) / W.  parts: iterable of (tsdf, weight, rgb or None) tensors (any device)."""
+    parts = list(parts)
+    s = sum(t * w - 1.0 for t, w, _ in parts)
+    wsum = sum(w - 1.0 for _, w, _ in parts)
+    W = 1.0 + wsum
+    rgb = None
+    if parts[0][2] is not None:
+        rgb = sum(c * w.unsqueeze(-1) for _, w, c in parts) / W.unsqueeze(-1)
+    return (1.0 + s) / W, W, rgb
+
+
+class BoundedTSDFVolume:
+    """Dense bounded TSDF volume on one GPU.
+
+        vol = BoundedTSDFVolume(origin, voxel_size, (nx, ny, nz), sdf_trunc, depth_trunc, with_rgb=True)
+        vol.integrate(full_proj_transforms, depthmaps, rgbmaps)       # as often as views arrive
+        vol.reduce_to(0)                                              # config 5: sum the per-tile volumes on rank 0
+        sdf = vol.tsdf                                                # (nz, ny, nx) lattice for marching cubes
+
+    Lattice point (ix, iy, iz) = origin + (ix, iy, iz) * voxel_size; ``tsdf`` / ``weight`` are (nz, ny, nx), ``rgb``
+    (nz, ny, nx, 3): the array layout marching-cubes implementations take (mcube_utils.py:57-68 reshapes its samples the
+    same way)."""
+
+    def __init__(self, origin, voxel_size, dims, sdf_trunc, depth_trunc, with_rgb=False, device=None):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BoundedTSDFVolume needs a CUDA device (gsr_b200 has no CPU path)")
+        self.nx, self.ny, self.nz = (int(v) for v in dims)
+        self.voxel_size, self.sdf_trunc, self.depth_trunc = float(voxel_size), float(sdf_trunc), float(depth_trunc)
+        self._origin = (ctypes.c_float * 3)(*[float(v) for v in origin])
+        shape = (self.nz, self.ny, self.nx)
+        self.tsdf = torch.empty(shape, dtype=torch.float32, device=self.device)
+        self.weight = torch.empty(shape, dtype=torch.float32, device=self.device)
+        self.rgb = torch.empty(shape + (3,), dtype=torch.float32, device=self.device) if with_rgb else None
+        self._fresh = True
+
+    @torch.no_grad()
+    def integrate(self, full_proj_transforms, depthmaps, rgbmaps=None):
+        if (rgbmaps is not None) != (self.rgb is not None):
+            raise ValueError("rgbmaps must be given exactly when the volume was created with_rgb=True")
+        views = TSDFFusion(full_proj_transforms, depthmaps, rgbmaps, device=self.device)
+        with on_device(self.device):
+            for v0, nv in views._launch_groups(4 if rgbmaps is not None else 1):
+                check(lib().gsr_tsdf_integrate_grid(
+                    self.nx, self.ny, self.nz, self._origin, self.voxel_size, self.sdf_trunc, self.depth_trunc, nv,
+                    (views._views.data_ptr() + _VIEW_BYTES * v0) if nv else None, int(self._fresh), self.tsdf.data_ptr(),
+                    self.weight.data_ptr(), self.rgb.data_ptr() if self.rgb is not None else None, stream_ptr(self.device)),
+                    "gsr_tsdf_integrate_grid")
+                self._fresh = False
+        torch.cuda.current_stream(self.device).synchronize()      # the view maps owned by `views` may be freed now
+        return self
+
+    @torch.no_grad()
+    def reduce_to(self, dst=0, group=None):
+        """Sum the partial volumes of all ranks on `dst` (NCCL reduce over NVLink; the only collective of the path:
+        north_star's "final mesh gather").  A rank that integrated nothing contributes the initial state.  After the call
+        rank `dst` holds the volume of ALL ranks' views; the other ranks' buffers are left as they were."""
+        if self._fresh:
+            self.integrate([], [], [] if self.rgb is not None else None)
+        out = reduce_partial_volume(self.tsdf, self.weight, self.rgb, dst, group)
+        if out is not None:
+            self.tsdf, self.weight, self.rgb = out
+        return self
+
+
+def reduce_partial_volume(tsdf, weight, rgb=None, dst=0, group=None):
+    """torch.distributed reduce of one partial volume per rank (tensors on any device: NCCL for CUDA, gloo for CPU).
+    Sends (tsdf*w - 1, w - 1[, rgb*w]) -- 8 (20) bytes per voxel -- and returns the combined (tsdf, weight, rgb) on rank
+    `dst`, None elsewhere.  Exact up to float rounding: see combine_partial_volumes."""
+    import torch.distributed as dist
+    s = tsdf * weight - 1.0
+    w = weight - 1.0
+    dist.reduce(s, dst, op=dist.ReduceOp.SUM, group=group)
+    dist.reduce(w, dst, op=dist.ReduceOp.SUM, group=group)
+    c = None
+    if rgb is not None:
+        c = rgb * weight.unsqueeze(-1)
+        dist.reduce(c, dst, op=dist.ReduceOp.SUM, group=group)
+    if dist.get_rank(group) != dst:
+        return None
+    W = 1.0 + w
+    return (1.0 + s) / W, W, (c / W.unsqueeze(-1) if c is not None else None)

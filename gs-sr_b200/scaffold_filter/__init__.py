@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from gsr_b200 import check, lib, ptr
 from gsr_b200._torch_util import f32c, on_device, stream_ptr
+from gsr_b200._torch_util import check_per_gaussian
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -55,6 +56,7 @@ class GaussianRasterizer(nn.Module):
                 sc = f32c(scales, "scales", dev)
                 if sc is not None and sc.numel() and sc.shape[-1] != 3:
                     raise RuntimeError("scales must have shape (P, 3)")
+                check_per_gaussian(P, scales=(sc, [(3,)]), rotations=(rotations, [(4,)]), cov3D_precomp=(cov3D_precomp, [(6,)]))
                 with on_device(dev):
                     check(lib().gsr_visible_filter(
                         P, int(rs.image_width), int(rs.image_height), ptr(f32c(means3D, "means3D", dev)), ptr(sc),

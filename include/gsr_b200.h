@@ -60,7 +60,8 @@ const char* gsr_build_arch(void);
  * each launch of the next forward/backward calls (bench.py's roofline numbers).
  * gsr_profile_read() fills GSR_PROF_SLOTS floats (milliseconds, -1 = not run) for the
  * most recent call of each kernel; it blocks on the recorded events.
- * Not thread-safe; off by default. */
+ * Events are kept per device (enable / read act on the CURRENT device); the on/off switch is
+ * process-wide.  A measurement hook, not part of the re-entrant per-stream path; off by default. */
 enum {
     GSR_PROF_PREPROCESS_FWD = 0,
     GSR_PROF_SCAN = 1,
@@ -236,7 +237,8 @@ int gsr_plane_backward(int P, int D, int M, int R, const float* background,
  * (F/cuda_rasterizer/rasterizer.h:56-72, F/cuda_rasterizer/rasterizer_impl.cu:340-396)
  * as called from RasterizeGaussiansfilterCUDA (F/rasterize_points.cu:220-284).
  * radii (P) int32 is fully written; needs no scratch (the reference still resizes
- * its geometry and image chunks). */
+ * its geometry and image chunks).  `prefiltered` is accepted for signature parity and ignored
+ * (no flag word / read-back on this asynchronous entry point; the reference traps in-kernel). */
 int gsr_visible_filter(int P, int width, int height, const float* means3D, const float* scales,
                        float scale_modifier, const float* rotations, const float* cov3D_precomp,
                        const float* viewmatrix, const float* projmatrix, float tan_fovx,
@@ -281,6 +283,19 @@ typedef struct gsr_tsdf_view {
 int gsr_tsdf_fuse(long long n, const float* samples, int contracted, const float* center_host3,
                   float radius, float voxel_size, int nviews, const gsr_tsdf_view* views, int init,
                   float* tsdf, float* weights, float* rgb, void* stream);
+
+/* Bounded TSDF volume: the fusion of GaussianExtractor.extract_mesh_bounded (gssr/utils/mesh_utils.py:138-179) and of the
+ * multi-tile extract_mesh_split.py:81-119 on a dense nx x ny x nz lattice  origin + (ix, iy, iz) * voxel_size  (x fastest).
+ * The reference delegates this to Open3D's ScalableTSDFVolume (absent third-party dependency, no vectors in the
+ * reference: PARITY UNPINNED against Open3D); the integration rule used here is the reference's own torch rule
+ * (gsr_tsdf_fuse above: project with full_proj_transform, bilinear depth sample, sdf = depth - z, running mean where
+ * sdf > -sdf_trunc, start tsdf = 1 / weight = 1 / rgb = 0) with the two masks of the bounded path: a view is skipped
+ * where its sampled depth is <= 0 (masked background, :160-162) or > depth_trunc (:165-170).
+ * init != 0 starts a fresh volume, init == 0 continues from tsdf / weights / rgb ((nz,ny,nx) floats, rgb (nz,ny,nx,3) or NULL).
+ * Volumes fused on different GPUs (one VastGaussian tile each) combine exactly: sum over ranks of (tsdf*w - 1, w - 1, rgb*w). */
+int gsr_tsdf_integrate_grid(int nx, int ny, int nz, const float* origin_host3, float voxel_size, float sdf_trunc,
+                            float depth_trunc, int nviews, const gsr_tsdf_view* views, int init, float* tsdf,
+                            float* weights, float* rgb, void* stream);
 
 /* ---- fused SSIM loss (image-space step right after the rasterizer) ---------------------- */
 

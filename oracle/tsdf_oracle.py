@@ -92,3 +92,44 @@ def compute_unbounded_tsdf(samples, contracted, center, radius, voxel_size, proj
     if return_rgb:
         return tsdfs, rgbs
     return tsdfs
+
+
+def integrate_grid(origin, voxel_size, dims, sdf_trunc, depth_trunc, projs, depthmaps, rgbmaps=None, state=None):
+    """Bounded volume (extract_mesh_bounded, mesh_utils.py:138-179, with the torch rule above standing in for Open3D's
+    ScalableTSDFVolume -- parity unpinned against Open3D): lattice origin + (ix, iy, iz) * voxel_size, x fastest; fixed
+    truncation; a view is skipped where its sampled depth is <= 0 (:160-162) or > depth_trunc (:165-170).
+    Returns (tsdf, weight, rgb) shaped (nz, ny, nx[, 3]); `state` continues an earlier call."""
+    nx, ny, nz = dims
+    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    o = np.asarray(origin, dtype=F)
+    pts = np.stack([ix.ravel().astype(F) * F(voxel_size) + o[0], iy.ravel().astype(F) * F(voxel_size) + o[1],
+                    iz.ravel().astype(F) * F(voxel_size) + o[2]], axis=-1).astype(F)
+    n = pts.shape[0]
+    if state is None:
+        tsdfs, weights, rgbs = np.ones(n, dtype=F), np.ones(n, dtype=F), np.zeros((n, 3), dtype=F)
+    else:
+        tsdfs, weights = state[0].reshape(-1).copy(), state[1].reshape(-1).copy()
+        rgbs = state[2].reshape(-1, 3).copy() if state[2] is not None else np.zeros((n, 3), dtype=F)
+    hom = np.concatenate([pts, np.ones((n, 1), dtype=F)], axis=-1)
+    trunc = F(sdf_trunc)
+    for v, M in enumerate(projs):
+        new_points = (hom @ np.asarray(M, dtype=F)).astype(F)
+        z = new_points[:, 3]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            pix = (new_points[:, :2] / z[:, None]).astype(F)
+        mask_proj = (pix > -1).all(-1) & (pix < 1).all(-1) & (z > 0)
+        gx = np.where(mask_proj, pix[:, 0], F(0)).astype(F)
+        gy = np.where(mask_proj, pix[:, 1], F(0)).astype(F)
+        d = grid_sample_border(np.asarray(depthmaps[v], dtype=F).reshape(depthmaps[v].shape[-2:]), gx, gy)
+        sdf = d - z
+        mask = mask_proj & (d > 0) & (d <= F(depth_trunc)) & (sdf > -trunc)
+        s = np.clip(sdf / trunc, F(-1), F(1)).astype(F)
+        w = weights[mask]
+        wp = w + F(1)
+        tsdfs[mask] = (tsdfs[mask] * w + s[mask]) / wp
+        if rgbmaps is not None:
+            rgb = np.stack([grid_sample_border(np.asarray(rgbmaps[v][c], dtype=F), gx, gy) for c in range(3)], -1)
+            rgbs[mask] = (rgbs[mask] * w[:, None] + rgb[mask]) / wp[:, None]
+        weights[mask] = wp
+    shape = (nz, ny, nx)
+    return tsdfs.reshape(shape), weights.reshape(shape), (rgbs.reshape(shape + (3,)) if rgbmaps is not None else None)

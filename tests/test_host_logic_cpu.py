@@ -65,3 +65,20 @@ def test_python_mirrors_reject_cpu_tensors_without_touching_the_gpu():
         surfel_postprocess(torch.zeros(11, 8, 8), torch.eye(4), torch.eye(4))
     with pytest.raises(NotImplementedError):
         ssim(torch.zeros(3, 8, 8), torch.zeros(3, 8, 8), window_size=7)
+
+
+def test_per_gaussian_shape_checks():
+    """A tensor left behind by a densify / prune desync must raise on the host, not read out of bounds on the device."""
+    import torch
+    from gsr_b200._torch_util import check_per_gaussian
+    P = 5
+    ok = dict(opacities=(torch.zeros(P, 1), [(1,), ()]), rotations=(torch.zeros(P, 4), [(4,)]), sh=(torch.zeros(P, 16, 3), [(None, 3)]),
+              colors_precomp=(torch.zeros(0), [(3,)]), scales=(None, [(2,)]))
+    check_per_gaussian(P, **ok)
+    check_per_gaussian(P, opacities=(torch.zeros(P), [(1,), ()]))
+    with pytest.raises(RuntimeError, match="rotations has 4 rows, expected 5"):
+        check_per_gaussian(P, rotations=(torch.zeros(4, 4), [(4,)]))
+    with pytest.raises(RuntimeError, match="sh has shape"):
+        check_per_gaussian(P, sh=(torch.zeros(P, 16, 4), [(None, 3)]))
+    with pytest.raises(RuntimeError, match="scales has shape"):
+        check_per_gaussian(P, scales=(torch.zeros(P, 3), [(2,)]))

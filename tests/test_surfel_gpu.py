@@ -192,6 +192,36 @@ def test_bucketed_tile_sort_gives_the_bitonic_order():
     assert np.array_equal(a["radii"], b["radii"])
 
 
+@pytest.mark.parametrize("P", [3000, 12000])
+def test_heavy_tiles_take_the_large_sort_paths(P):
+    """Thousands of low-opacity splats stacked on ONE tile: its list has > 2048 entries (shared-memory bitonic network,
+    tile_sort.cuh) resp. > 4096 (in-place global-memory bitonic sort) and is blended > 1000 entries deep, so every part of
+    the sorted order matters.  Product vs the CPU oracle, and the bucketed-sort fallback flag against the default."""
+    import gsr_b200
+    W = H = 64
+    sc = synth.make_scene(P, W, H, seed=91, sigma_px=1.0)
+    rng = np.random.default_rng(92)
+    f = 1.2 * W
+    z = sc.means3D[:, 2].astype(np.float64)
+    u, v = rng.uniform(20.0, 28.0, P), rng.uniform(20.0, 28.0, P)          # all centres inside tile (1, 1)
+    sc.means3D[:, 0] = ((u - W / 2) * z / f).astype(np.float32)
+    sc.means3D[:, 1] = ((v - H / 2) * z / f).astype(np.float32)
+    sc.opacities[:] = rng.uniform(0.006, 0.02, (P, 1)).astype(np.float32)
+    gc, go = synth.make_upstream_grads(W, H, seed=93)
+    out = hz.run_product_surfel(sc, gc, go)
+    orc = hz.run_oracle_surfel(sc, gc, go)
+    tile11 = out["others"][1][16:32, 16:32]
+    assert tile11.min() > 0.5                                             # deep blend everywhere in the heavy tile
+    assert_forward_close(out, orc)
+    assert_grads_close(out["grads"], orc["grads"], ["opacities", "colors", "means3D"])
+    gsr_b200.lib().gsr_set_option(b"dbg", 1)                              # bitonic network for every tile
+    try:
+        alt = hz.run_product_surfel(sc, gc, go)
+    finally:
+        gsr_b200.lib().gsr_set_option(b"dbg", 0)
+    assert np.array_equal(alt["color"], out["color"]) and np.array_equal(alt["others"], out["others"])
+
+
 def test_product_matches_reference_cuda_build():
     from oracle import refcuda
     if not refcuda.available("surfel"):

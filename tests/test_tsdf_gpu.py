@@ -93,3 +93,55 @@ def test_full_chunk_identities():
     check(L.gsr_tsdf_fuse(n, pts.data_ptr(), 1, f._center, f.radius, float(c["voxel_size"]), f.nviews - half,
                           f._views.data_ptr() + 96 * half, 0, ts.data_ptr(), ws.data_ptr(), None, s), "gsr_tsdf_fuse")
     assert torch.equal(ts, t)
+
+
+# ---- bounded volume (extract_mesh_bounded / extract_mesh_split) ------------------------------------------------------------
+GRID = dict(origin=(-0.8, -0.8, -0.8), voxel_size=0.05, dims=(33, 30, 29), sdf_trunc=0.2, depth_trunc=4.0)
+
+
+def _views(c, sl=slice(None)):
+    return ([torch.from_numpy(m) for m in c["projs"][sl]], [torch.from_numpy(d) for d in c["depthmaps"][sl]],
+            [torch.from_numpy(r) for r in c["rgbmaps"][sl]])
+
+
+@pytest.mark.parametrize("with_rgb", [False, True])
+def test_bounded_volume_matches_oracle(with_rgb):
+    """gsr_tsdf_integrate_grid against the numpy restatement of the same rule (the reference's torch rule on a bounded
+    lattice + the depth <= 0 / > depth_trunc masks of mesh_utils.py:160-170; Open3D itself is absent: parity unpinned)."""
+    from gsr_b200.tsdf import BoundedTSDFVolume
+    from oracle import tsdf_oracle
+    c = build_tsdf_case("ragged")
+    vol = BoundedTSDFVolume(with_rgb=with_rgb, **GRID)
+    p, d, r = _views(c)
+    vol.integrate(p, d, r if with_rgb else None)
+    ot, ow, orgb = tsdf_oracle.integrate_grid(projs=c["projs"], depthmaps=c["depthmaps"], rgbmaps=c["rgbmaps"] if with_rgb else None, **GRID)
+    assert vol.tsdf.shape == (29, 30, 33)
+    t, w = vol.tsdf.cpu().numpy(), vol.weight.cpu().numpy()
+    flips = (w != ow)                                  # a sample within rounding of the truncation / frustum / depth mask
+    assert flips.mean() <= 1e-3
+    assert np.abs(t - ot)[~flips].max() <= 1e-4
+    if with_rgb:
+        assert np.abs(vol.rgb.cpu().numpy() - orgb)[~flips].max() <= 1e-4
+    assert (w > 1).mean() > 0.05 and (t < 0).any() and (t > 0.5).any()          # the surface is inside the volume
+
+
+def test_bounded_volume_streams_views_and_combines_like_two_gpus():
+    """Views integrated in several calls == one call; two volumes fused from disjoint view sets (one VastGaussian tile per
+    GPU) combined with the reduce algebra == one volume fused from all views."""
+    from gsr_b200.tsdf import BoundedTSDFVolume, combine_partial_volumes
+    c = build_tsdf_case("world_rgb", n=8)
+    p, d, r = _views(c)
+    full = BoundedTSDFVolume(with_rgb=True, **GRID).integrate(p, d, r)
+    streamed = BoundedTSDFVolume(with_rgb=True, **GRID)
+    for sl in (slice(0, 2), slice(2, 5)):
+        streamed.integrate(*_views(c, sl))
+    assert torch.equal(streamed.tsdf, full.tsdf) and torch.equal(streamed.weight, full.weight) and torch.equal(streamed.rgb, full.rgb)
+    a = BoundedTSDFVolume(with_rgb=True, **GRID).integrate(*_views(c, slice(0, 3)))
+    b = BoundedTSDFVolume(with_rgb=True, **GRID).integrate(*_views(c, slice(3, 5)))
+    t, w, rgb = combine_partial_volumes([(a.tsdf, a.weight, a.rgb), (b.tsdf, b.weight, b.rgb)])
+    assert torch.equal(w, full.weight)
+    assert float((t - full.tsdf).abs().max()) <= 2e-6 and float((rgb - full.rgb).abs().max()) <= 2e-6
+    empty = BoundedTSDFVolume(with_rgb=False, **GRID).integrate([], [])
+    assert float(empty.tsdf.min()) == 1.0 and float(empty.weight.max()) == 1.0
+    with pytest.raises(ValueError):
+        BoundedTSDFVolume(with_rgb=False, **GRID).integrate(p, d, r)

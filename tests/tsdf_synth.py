@@ -112,4 +112,5 @@ def build_tsdf_case(name, n=None):
         contracted = True
         voxel = 2 * radius / 256
     return dict(samples=samples, contracted=contracted, center=center, radius=radius, voxel_size=voxel,
-                projs=[c["full_proj"] for c in cams], depthmaps=[m[0] for m in maps], rgbmaps=[m[1] for m in maps])
+                projs=[c["full_proj"] for c in cams], depthmaps=[m[0] for m in maps], rgbmaps=[m[1] for m in maps],
+                eyes=np.array(eyes, dtype=np.float64))
