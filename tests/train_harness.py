@@ -392,10 +392,13 @@ class MiniPGSRTrainer(MiniTwoDGSTrainer):
         n = F.normalize(torch.cross(l2r, b2t, dim=-1), p=2, dim=-1)
         return F.pad(n.permute(2, 0, 1), (1, 1, 1, 1), mode="constant")
 
+    def gaussians_for_view(self, vi):
+        return (self.xyz, torch.sigmoid(self.opacity), torch.exp(self.scaling), F.normalize(self.rotation),
+                torch.sigmoid(self.colors_raw))
+
     def render_view(self, vi):
         cam = self.cams[vi]
-        means3D, opacity = self.xyz, torch.sigmoid(self.opacity)
-        scales, rotations, colors = torch.exp(self.scaling), F.normalize(self.rotation), torch.sigmoid(self.colors_raw)
+        means3D, opacity, scales, rotations, colors = self.gaussians_for_view(vi)
         sp = torch.zeros_like(means3D, requires_grad=True) + 0
         sp_abs = torch.zeros_like(means3D, requires_grad=True) + 0
         sp.retain_grad(); sp_abs.retain_grad()
@@ -428,7 +431,7 @@ class MiniPGSRTrainer(MiniTwoDGSTrainer):
             depth_normal = self.normal_from_depth(plane_depth.squeeze(), cam) * rendered_alpha.detach()
         return dict(render=image, viewspace_points=sp, viewspace_points_abs=sp_abs, visibility_filter=radii > 0, radii=radii,
                     out_observe=observe, rendered_normal=rendered_normal, plane_depth=plane_depth,
-                    rendered_distance=out_all_map[4:5], depth_normal=depth_normal)
+                    rendered_distance=out_all_map[4:5], depth_normal=depth_normal, scaling=scales)
 
     def step(self):
         ref, near = self.render_view(0), self.render_view(1)
@@ -454,9 +457,221 @@ class MiniPGSRTrainer(MiniTwoDGSTrainer):
         return loss_value, {k_: float(v.detach()) for k_, v in losses.items()}
 
 
+# ---- octree variants (BASELINE configs 4 and 5) and anchor growing ------------------------------------------------------
+class OctreeMixin:
+    """Level-of-detail anchors of OctreeGaussian, restated: every anchor carries an integer `level`; per view,
+    set_anchor_mask keeps the anchors whose level does not exceed the level predicted from the camera distance
+    (gssr/gaussian/octree_gaussian.py:184-196 dist2level='round', :255-267), prefilter_voxel runs visible_filter on
+    the masked anchors only and scatters the result back (gssr/scene/octree_scene.py:136-172), and the MLPs see the level
+    as an extra input (add_level, octree_scene.py:42-66)."""
+    fork, levels = 2, 4
+
+    def init_octree(self, n_anchor, seed):
+        g = torch.Generator(device="cpu").manual_seed(seed + 7)
+        self.level = torch.randint(0, self.levels, (n_anchor, 1), generator=g).to(self.device)
+        self.extra_level = torch.zeros(n_anchor, device=self.device)
+        self.voxel_size = 0.01
+        d = (self.anchor.detach() - self.campos).norm(dim=1)
+        self.standard_dist = float(d.quantile(0.25))                     # nearer anchors may use the finest levels
+        self.anchor_mask = torch.ones(n_anchor, dtype=torch.bool, device=self.device)
+
+    def set_anchor_mask(self, cam_center, resolution_scale=1.0):
+        anchor_pos = self.anchor + (self.voxel_size / 2) / (float(self.fork) ** self.level)
+        dist = torch.sqrt(torch.sum((anchor_pos - cam_center) ** 2, dim=1)) * resolution_scale
+        pred_level = torch.log2(self.standard_dist / dist) / math.log2(self.fork) + self.extra_level
+        int_level = torch.clamp(torch.round(pred_level).int(), min=0, max=self.levels - 1)
+        self.anchor_mask = (self.level.squeeze(dim=1) <= int_level)
+
+    def octree_prefilter(self, view, proj, campos, tanfovx, tanfovy):
+        anchor_mask = self.anchor_mask
+        means3D = self.anchor[anchor_mask]
+        scales = torch.exp(self.scaling)[anchor_mask]
+        rotations = self.rotation[anchor_mask]
+        if self.impl == "ours":
+            fs = self.filter_mod.GaussianRasterizationSettings(self.H, self.W, tanfovx, tanfovy, self.bg, 1.0, view, proj, 0, campos,
+                                                               False, False)
+            radii_pure = self.filter_mod.GaussianRasterizer(fs).visible_filter(means3D=means3D, scales=scales[:, :3],
+                                                                               rotations=rotations, cov3D_precomp=None)
+        else:
+            from oracle.refcuda import ref_visible_filter
+            radii_pure = ref_visible_filter(means3D.detach().contiguous(), scales[:, :3].detach().contiguous(), rotations.contiguous(),
+                                            view, proj, self.W, self.H, tanfovx, tanfovy)
+        visible_mask = anchor_mask.clone()
+        visible_mask[anchor_mask] = radii_pure > 0
+        return visible_mask
+
+
+class MiniOctree2DGSTrainer(OctreeMixin, MiniScaffold2DGSTrainer):
+    """Octree-2DGS iteration (BASELINE config 5's per-tile model; octree_2dgs_scene.py:11-27 = TwoDGSScene + OctreeScene):
+    set_anchor_mask -> octree prefilter_voxel -> neural Gaussians with the level input -> surfel rasterizer on the
+    stride-3 scaling[:, :2] view -> 2DGS + scaling losses -> anchor statistics."""
+
+    def __init__(self, n_anchor=200_000, k=5, feat_dim=32, **kw):
+        super().__init__(n_anchor=n_anchor, k=k, feat_dim=feat_dim, **kw)
+        self.init_octree(n_anchor, kw.get("seed", 0))
+        torch.manual_seed(kw.get("seed", 0) + 3)
+        mlp = lambda o, act: torch.nn.Sequential(torch.nn.Linear(feat_dim + 3 + 1, feat_dim), torch.nn.ReLU(True),  # noqa: E731
+                                                 torch.nn.Linear(feat_dim, o), act).to(self.device)
+        self.mlp_opacity, self.mlp_color, self.mlp_cov = mlp(k, torch.nn.Tanh()), mlp(3 * k, torch.nn.Sigmoid()), mlp(7 * k, torch.nn.Identity())
+        params = [self.anchor, self.scaling, self.offset, self.anchor_feat] + [p for m in (self.mlp_opacity, self.mlp_color, self.mlp_cov) for p in m.parameters()]
+        self.optimizer = torch.optim.Adam(params, lr=1e-3, eps=1e-15)
+
+    def prefilter_voxel(self):
+        self.set_anchor_mask(self.campos)
+        return self.octree_prefilter(self.view, self.proj, self.campos, self.sc.cam.tanfovx, self.sc.cam.tanfovy)
+
+    def generate_neural_gaussians(self, visible_mask):
+        k = self.k
+        feat, anchor, level = self.anchor_feat[visible_mask], self.anchor[visible_mask], self.level[visible_mask].float()
+        grid_offsets, grid_scaling = self.offset[visible_mask], torch.exp(self.scaling)[visible_mask]
+        ob_view = anchor - self.campos
+        ob_view = ob_view / ob_view.norm(dim=1, keepdim=True)
+        x = torch.cat([feat, ob_view, level], dim=1)
+        neural_opacity = self.mlp_opacity(x).reshape([-1, 1])
+        mask = (neural_opacity > 0.0).view(-1)
+        opacity = neural_opacity[mask]
+        color = self.mlp_color(x).reshape([anchor.shape[0] * k, 3])
+        scale_rot = self.mlp_cov(x).reshape([anchor.shape[0] * k, 7])
+        rep = torch.cat([grid_scaling, anchor], dim=-1).repeat_interleave(k, dim=0)
+        masked = torch.cat([rep, color, scale_rot, grid_offsets.view([-1, 3])], dim=-1)[mask]
+        scaling_repeat, repeat_anchor, color, scale_rot, offsets = masked.split([6, 3, 3, 7, 3], dim=-1)
+        scaling = scaling_repeat[:, 3:] * torch.sigmoid(scale_rot[:, :3])
+        rot = F.normalize(scale_rot[:, 3:7])
+        xyz = repeat_anchor + offsets * scaling_repeat[:, :3]
+        return xyz, color, opacity, scaling, rot, neural_opacity, mask
+
+
+class MiniOctreePGSRTrainer(OctreeMixin, MiniPGSRTrainer):
+    """Octree-PGSR iteration (BASELINE config 4; octree_pgsr_scene.py:13-47 = PGSRScene + OctreeScene): per view
+    set_anchor_mask + octree prefilter + neural Gaussians, rendered through the plane rasterizer with the autograd-built
+    all_map; PGSR losses + scaling loss; anchor statistics from the reference view."""
+
+    def __init__(self, n_anchor=100_000, k=5, feat_dim=32, W=800, H=450, seed=0, impl="ours", device="cuda"):
+        super().__init__(P=n_anchor, W=W, H=H, seed=seed, impl=impl, device=device)
+        self.k = k
+        sc = self.sc
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        g = torch.Generator(device="cpu").manual_seed(seed + 1)
+        self.anchor = torch.nn.Parameter(t(sc.means3D))
+        base = torch.log(t(sc.scales).mean(dim=1, keepdim=True) * 2.0)
+        self.scaling = torch.nn.Parameter(base.repeat(1, 6).contiguous())
+        self.rotation = torch.nn.Parameter(t(sc.rotations), requires_grad=False)
+        self.offset = torch.nn.Parameter((torch.randn((n_anchor, k, 3), generator=g) * 0.5).to(device))
+        self.anchor_feat = torch.nn.Parameter((torch.randn((n_anchor, feat_dim), generator=g) * 0.5).to(device))
+        self.campos = self.cams[0]["campos"]
+        self.init_octree(n_anchor, seed)
+        torch.manual_seed(seed + 2)
+        mlp = lambda o, act: torch.nn.Sequential(torch.nn.Linear(feat_dim + 3 + 1, feat_dim), torch.nn.ReLU(True),  # noqa: E731
+                                                 torch.nn.Linear(feat_dim, o), act).to(device)
+        self.mlp_opacity, self.mlp_color, self.mlp_cov = mlp(k, torch.nn.Tanh()), mlp(3 * k, torch.nn.Sigmoid()), mlp(7 * k, torch.nn.Identity())
+        params = [self.anchor, self.scaling, self.offset, self.anchor_feat] + [p for m in (self.mlp_opacity, self.mlp_color, self.mlp_cov) for p in m.parameters()]
+        self.optimizer = torch.optim.Adam(params, lr=1e-3, eps=1e-15)
+        self.opacity_accum = torch.zeros((n_anchor, 1), device=device)
+        self.anchor_demon = torch.zeros((n_anchor, 1), device=device)
+        self.offset_gradient_accum = torch.zeros((n_anchor * k, 1), device=device)
+        self.offset_denom = torch.zeros((n_anchor * k, 1), device=device)
+        import scaffold_filter
+        self.filter_mod = scaffold_filter
+        self.lambda_scaling = 0.01
+
+    generate_neural_gaussians = MiniOctree2DGSTrainer.generate_neural_gaussians
+
+    def gaussians_for_view(self, vi):
+        cam = self.cams[vi]
+        self.campos = cam["campos"]
+        self.set_anchor_mask(cam["campos"])
+        visible = self.octree_prefilter(cam["view"], cam["proj"], cam["campos"], cam["tanfovx"], cam["tanfovy"])
+        xyz, color, opacity, scaling, rot, neural_opacity, mask = self.generate_neural_gaussians(visible)
+        self._stat = (visible, neural_opacity, mask) if vi == 0 else self._stat
+        return xyz, opacity, scaling, rot, color
+
+    def step(self):
+        ref, near = self.render_view(0), self.render_view(1)
+        image = ref["render"]
+        losses = {"L1_loss": (1.0 - self.lambda_dssim) * torch.abs(image - self.gt).mean(),
+                  "ssim_loss": self.lambda_dssim * (1.0 - self.ssim(image, self.gt)),
+                  "normal_loss": self.lambda_normal * ((ref["depth_normal"] - ref["rendered_normal"]).abs().sum(0)).mean(),
+                  "geo_loss": 0.03 * (ref["plane_depth"] - near["plane_depth"]).abs().clamp(max=1.0).mean(),
+                  "scaling_loss": self.lambda_scaling * ref["scaling"].prod(dim=1).mean()}
+        loss = sum(losses.values())
+        loss.backward()
+        loss_value = loss.item()
+        with torch.no_grad():                                           # scaffold_gaussian.py:488-508 on the reference view
+            visible, neural_opacity, mask = self._stat
+            update_filter = ref["radii"] > 0
+            temp_opacity = neural_opacity.clone().view(-1).detach()
+            temp_opacity[temp_opacity < 0] = 0
+            self.opacity_accum[visible] += temp_opacity.view([-1, self.k]).sum(dim=1, keepdim=True)
+            self.anchor_demon[visible] += 1
+            av = visible.unsqueeze(dim=1).repeat([1, self.k]).view(-1)
+            combined = torch.zeros_like(self.offset_gradient_accum, dtype=torch.bool).squeeze(dim=1)
+            combined[av] = mask
+            tmp = combined.clone()
+            combined[tmp] = update_filter
+            self.offset_gradient_accum[combined] += torch.norm(ref["viewspace_points"].grad[update_filter, :2], dim=-1, keepdim=True)
+            self.offset_denom[combined] += 1
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        self.last = dict(observed=int((ref["out_observe"] > 0).sum()), visible=int(visible.sum()), gaussians=int(mask.sum()))
+        return loss_value, {k_: float(v.detach()) for k_, v in losses.items()}
+
+
+def scatter_max_rows(src, index, n_out):
+    """torch_scatter.scatter_max(src, index[:, None].expand_as(src), dim=0)[0] (scaffold_gaussian.py:619): per output row the
+    column-wise maximum over the source rows mapped to it; rows nobody maps to stay 0."""
+    out = torch.zeros((n_out, src.shape[1]), dtype=src.dtype, device=src.device)
+    return out.scatter_reduce(0, index[:, None].expand_as(src), src, reduce="amax", include_self=False)
+
+
+def anchor_growing_candidates(tr, grad_threshold=0.0002, update_depth=3, update_init_factor=16, update_hierachy_factor=4,
+                              check_interval=100, success_threshold=0.8, seed=0):
+    """The selection half of ScaffoldGaussian.adjust_anchor / anchor_growing (gssr/gaussian/scaffold_gaussian.py:557-640,
+    :642-651): from the statistics the rasterizer's means2D gradients fed (offset_gradient_accum / offset_denom), the
+    voxel-snapped positions and max-pooled features of the anchors that would be added at each of the `update_depth`
+    levels.  Returns [(candidate_anchor (n,3), new_feat (n,F))]; deterministic given `seed` (the reference draws
+    torch.rand_like masks).  The optimizer surgery that follows in the reference (cat_tensors_to_optimizer) is not part
+    of what the rasterizer influences and is left out."""
+    k = tr.k
+    grads = tr.offset_gradient_accum / tr.offset_denom
+    grads[grads.isnan()] = 0.0
+    grads = torch.norm(grads, dim=-1)
+    offset_mask = (tr.offset_denom > check_interval * success_threshold * 0.5).squeeze(dim=1)
+    gen = torch.Generator(device=grads.device).manual_seed(seed)
+    scaling = torch.exp(tr.scaling)
+    out = []
+    for i in range(update_depth):
+        cur_threshold = grad_threshold * ((update_hierachy_factor // 2) ** i)
+        candidate_mask = (grads >= cur_threshold) & offset_mask
+        rand_mask = torch.rand(candidate_mask.shape, generator=gen, device=grads.device) > (0.5 ** (i + 1))
+        candidate_mask = candidate_mask & rand_mask
+        all_xyz = tr.anchor.unsqueeze(dim=1) + tr.offset * scaling[:, :3].unsqueeze(dim=1)
+        cur_size = tr.voxel_size * (update_init_factor // (update_hierachy_factor ** i))
+        grid_coords = torch.round(tr.anchor / cur_size).int()
+        selected_grid_coords = torch.round(all_xyz.view([-1, 3])[candidate_mask] / cur_size).int()
+        uniq, inverse = torch.unique(selected_grid_coords, return_inverse=True, dim=0)
+        # drop voxels that already hold an anchor (hash compare instead of the reference's chunked broadcast compare)
+        key = lambda c: (c[:, 0].long() * 73856093) ^ (c[:, 1].long() * 19349663) ^ (c[:, 2].long() * 83492791)  # noqa: E731
+        occupied = torch.isin(key(uniq), key(grid_coords))
+        exact = torch.zeros_like(occupied)
+        if occupied.any():                                              # confirm hash hits exactly
+            cand = uniq[occupied]
+            exact_hit = (cand.unsqueeze(1) == grid_coords[torch.isin(key(grid_coords), key(cand))].unsqueeze(0)).all(-1).any(-1)
+            exact[occupied] = exact_hit
+        keep = ~exact
+        candidate_anchor = uniq[keep] * cur_size
+        new_feat = tr.anchor_feat.unsqueeze(dim=1).repeat([1, k, 1]).view([-1, tr.anchor_feat.shape[1]])[candidate_mask]
+        new_feat = scatter_max_rows(new_feat, inverse, uniq.shape[0])[keep]
+        out.append((candidate_anchor, new_feat))
+    return out
+
+
 def measure_iters_per_s(impl, P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, scaffold=False, pgsr=False,
-                        fused_ssim=False, fused_post=False):
-    if pgsr:
+                        fused_ssim=False, fused_post=False, octree=False):
+    if octree and pgsr:
+        tr = MiniOctreePGSRTrainer(P, W=W, H=H, seed=seed, impl=impl)
+    elif octree:
+        tr = MiniOctree2DGSTrainer(P, W=W, H=H, seed=seed, impl=impl)
+    elif pgsr:
         tr = MiniPGSRTrainer(P, W=W, H=H, seed=seed, impl=impl)
     elif scaffold:
         tr = MiniScaffold2DGSTrainer(P, W=W, H=H, seed=seed, impl=impl)
