@@ -33,9 +33,8 @@ template <bool MARK>
 __global__ void surfel_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float*,
                                   uint32_t*, float*, float*, float4*);
 cudaError_t launch_surfel_render_bwd(bool, int, const uint32_t*, const float4*, size_t, int, int, int, const float*, const float*,
-                                     const uint32_t*, const float*, const float*, float*, cudaStream_t);
+                                     const uint32_t*, const float*, const float*, float*, int, cudaStream_t);
 int fwd_ctas_per_tile();
-int ewa_bwd_ctas_per_tile();
 template <bool kRadiiOnly>
 __global__ void ewa_preprocess_fwd(int, int, int, const float*, const float*, const float4*, const float*, const float*,
                                    const float*, const bool, const ViewParams, const float, const float, const float,
@@ -50,9 +49,8 @@ __global__ void ewa_build_records(const uint32_t*, uint64_t*, const EwaGeom*, co
 template <bool GEO>
 __global__ void ewa_render_fwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float, float*,
                                uint32_t*, float*, int*, float*, float*, float4*);
-template <int MODE, bool USED>
-__global__ void ewa_render_bwd(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-                               const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+cudaError_t launch_ewa_render_bwd(int, bool, int, const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
+                                  const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*, int, cudaStream_t);
 cudaError_t launch_surfel_audit(int, const uint32_t*, const float4*, size_t, int, int, int, const float*, const uint32_t*, uint32_t,
                                 float*, int*, int*, cudaStream_t);
 cudaError_t launch_ewa_audit(int, const uint32_t*, const float4*, size_t, int, int, int, const float*, const uint32_t*, uint32_t,
@@ -502,7 +500,7 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
         prof_begin(GSR_PROF_RENDER_BWD, s);
         GSR_CUDA_CHECK(launch_surfel_render_bwd(P < (1 << REC_USED_SHIFT) && !g_no_used_bits, ntiles, iw.tile_offset, bw.planes,
                                                 bw.plane_stride, W, H, vc.gx, background, iw.final_T, iw.n_contrib, dL_dpix,
-                                                dL_dothers, bw.gacc, s));
+                                                dL_dothers, bw.gacc, (g_dbg & 2) != 0, s));
         prof_end(GSR_PROF_RENDER_BWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }
@@ -739,21 +737,10 @@ static int ewa_backward(const EwaBwdArgs& a, const char* who) {
     if (R > 0) {
         prof_begin(GSR_PROF_RENDER_BWD, s);
         const bool used = P < (1 << REC_USED_SHIFT) && !g_no_used_bits;
-        const dim3 bgrid(ntiles * ewa_bwd_ctas_per_tile()), bblock(256 / ewa_bwd_ctas_per_tile());
-#define GSR_EWA_BWD(MODE, USED, AMP, DAM, DPD)                                                                               \
-    ewa_render_bwd<MODE, USED><<<bgrid, bblock, 0, s>>>(iw.tile_offset, bw.planes, bw.plane_stride, W, H, vc.gx, a.background, \
-                                                        focal_x, focal_y, iw.final_T, iw.n_contrib, AMP, a.dL_dpix, DAM, DPD, bw.gacc)
-        if (a.geo) {
-            if (used) GSR_EWA_BWD(2, true, a.all_map_pixels, a.dL_dout_all_map, a.dL_dout_plane_depth);
-            else GSR_EWA_BWD(2, false, a.all_map_pixels, a.dL_dout_all_map, a.dL_dout_plane_depth);
-        } else if (a.plane) {
-            if (used) GSR_EWA_BWD(1, true, nullptr, nullptr, nullptr);
-            else GSR_EWA_BWD(1, false, nullptr, nullptr, nullptr);
-        } else {
-            if (used) GSR_EWA_BWD(0, true, nullptr, nullptr, nullptr);
-            else GSR_EWA_BWD(0, false, nullptr, nullptr, nullptr);
-        }
-#undef GSR_EWA_BWD
+        GSR_CUDA_CHECK(launch_ewa_render_bwd(a.geo ? 2 : (a.plane ? 1 : 0), used, ntiles, iw.tile_offset, bw.planes, bw.plane_stride, W, H,
+                                             vc.gx, a.background, focal_x, focal_y, iw.final_T, iw.n_contrib,
+                                             a.geo ? a.all_map_pixels : nullptr, a.dL_dpix, a.geo ? a.dL_dout_all_map : nullptr,
+                                             a.geo ? a.dL_dout_plane_depth : nullptr, bw.gacc, (g_dbg & 2) != 0, s));
         prof_end(GSR_PROF_RENDER_BWD, s);
         GSR_CUDA_CHECK(cudaGetLastError());
     }

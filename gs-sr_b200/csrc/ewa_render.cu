@@ -224,71 +224,66 @@ template __global__ void ewa_render_fwd<true>(const uint32_t*, const float4*, si
                                               float*, uint32_t*, float*, int*, float*, float*, float4*);
 
 // ---- backward -----------------------------------------------------------------------------------
-// Transposed warp reduction of 16 per-lane values (see surfel_render_bwd.cu): afterwards lane L holds
-// the 32-lane sum of v[idx], idx = ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
-__device__ __forceinline__ float ewa_reduce16(float (&v)[16], int lane) {
-    {
-        const bool hi = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float send = hi ? v[i] : v[i + 8];
-            const float keep = hi ? v[i + 8] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULLMASK, send, 16);
-        }
-    }
-    {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float send = hi ? v[i] : v[i + 4];
-            const float keep = hi ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULLMASK, send, 8);
-        }
-    }
-    {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const float send = hi ? v[i] : v[i + 2];
-            const float keep = hi ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULLMASK, send, 4);
-        }
-    }
-    {
-        const bool hi = lane & 2;
-        const float send = hi ? v[0] : v[1];
-        const float keep = hi ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(FULLMASK, send, 2);
-    }
-    v[0] += __shfl_xor_sync(FULLMASK, v[0], 1);
-    return v[0];
+// Same two-phase scheme as surfel_render_bwd.cu.  Phase 1 (lane = pixel) walks the contributing splats back to front
+// and parks TWO numbers per (pixel, splat) pair in a per-warp shared-memory slot: v = G dL/dalpha and the blend weight
+// w.  Everything the reference accumulates per pair is linear in them once the splat's constants are factored out:
+//   dL/dopacity = sum v;  dL/dcolour = sum w dL/dpixel;  dL/dall_map = sum w dL/dout_all_map;
+//   dL/dmean2D, dL/dconic = opacity x (first / second MOMENTS of v about the splat centre) x conic terms
+//   (G/backward.cu:507-548: dG_ddelx = -G (a dx + b dy), dL_dconic = -0.5 G d d^T dL_dG).
+// Phase 2 (lane = pending splat x half of the block's pixels) therefore only accumulates 6 moments of v and the
+// colour / all_map sums with one FMA each, shifts the moments from block-local pixel coordinates to the splat centre
+// once per splat, and flushes with 128-bit red.global.add.v4.  |dL/dmean2D| (plane) is the one non-linear sum: it takes
+// the absolute value per pair inside phase 2.  All linear per-pixel channels share one "blended behind" recurrence
+// (S_i = <channel values of splat i, upstream grads>, rec <- rec + alpha (S - rec)), see surfel_render_bwd.cu.
+__device__ __forceinline__ void ewa_red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // MODE 0: 3DGS (9 sums)   1: plane without render_geo (+ |dL_dmean2D|, 11 sums)   2: plane with render_geo (16 sums)
-// CTA = 4 warps = half a tile (16x8 px), 3-stage record ring, warps decoupled (the last warp to arrive on a stage
-// refills it; no __syncthreads() in the walk) -- same scheme as surfel_render_bwd.cu.
-constexpr int EWA_BWD_WARPS = 4, EWA_BWD_SPLIT = 8 / EWA_BWD_WARPS, EWA_BWD_STAGES = 3;
+#ifndef GSR_EWA_BWD_MINB
+#define GSR_EWA_BWD_MINB 3
+#endif
+#ifndef GSR_EWA_BWD_WARPS
+#define GSR_EWA_BWD_WARPS 8
+#endif
+constexpr int EWA_BWD_WARPS = GSR_EWA_BWD_WARPS, EWA_BWD_SPLIT = 8 / EWA_BWD_WARPS, EWA_BWD_STAGES = 4, EWA_BWD_BATCH = 32;
+constexpr int EWA_SLOTS = 16, EWA_LPS = 32 / EWA_SLOTS, EWA_PPL = 32 / EWA_LPS;     // pending pairs per warp; lanes / pixels per pair in phase 2
+constexpr int EWA_SLOT_STRIDE = 32 * 2 + 2;                                           // words; (stride / 2) odd
 int ewa_bwd_ctas_per_tile() { return EWA_BWD_SPLIT; }
+template <int MODE>
+constexpr size_t ewa_bwd_smem() {
+    return (size_t)EWA_BWD_STAGES * (MODE == 2 ? EWA_PLANES_GEO : EWA_PLANES) * EWA_BWD_BATCH * 16      // ring
+           + (size_t)EWA_BWD_WARPS * EWA_SLOTS * EWA_SLOT_STRIDE * 4                                     // pending pairs
+           + (size_t)EWA_BWD_WARPS * EWA_SLOTS * 32                                                      // slot headers
+           + (size_t)EWA_BWD_WARPS * EWA_LPS * (EWA_PPL * (MODE == 2 ? 2 : 1) + 1) * 16 + 128;           // pixel constants, misc
+}
 
 // USED: walk the forward's "blended" marks in the record word instead of repeating the cull test (P < 2^23)
 template <int MODE, bool USED>
-__global__ void __launch_bounds__(EWA_BWD_WARPS * 32, 6)
+__global__ void __launch_bounds__(EWA_BWD_WARPS * 32, GSR_EWA_BWD_MINB)
 ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W, int H,
                int gx, const float* __restrict__ bg, float focal_x, float focal_y, const float* __restrict__ final_T,
                const uint32_t* __restrict__ n_contrib, const float* __restrict__ all_map_pixels,
                const float* __restrict__ dL_dpix, const float* __restrict__ dL_dout_all_map,
-               const float* __restrict__ dL_dout_plane_depth, float* __restrict__ gacc) {
+               const float* __restrict__ dL_dout_plane_depth, float* __restrict__ gacc, int sync_ring) {
     constexpr bool GEO = MODE == 2;
     constexpr int NPL = GEO ? EWA_PLANES_GEO : EWA_PLANES;
-    constexpr int NV = MODE == 0 ? 9 : (MODE == 1 ? 11 : 16);
-    __shared__ __align__(128) float4 sbuf[EWA_BWD_STAGES][NPL][RBATCH];
-    __shared__ __align__(8) uint64_t full_bar[EWA_BWD_STAGES];
-    __shared__ int s_arrive[EWA_BWD_STAGES];
-    __shared__ int s_maxlast;
+    constexpr int PIXV = GEO ? 2 : 1;                 // float4 of upstream gradients per pixel
+    extern __shared__ __align__(128) unsigned char ewa_smem[];
+    float4(*sbuf)[NPL][EWA_BWD_BATCH] = reinterpret_cast<float4(*)[NPL][EWA_BWD_BATCH]>(ewa_smem);
+    constexpr size_t O_PEND = (size_t)EWA_BWD_STAGES * NPL * EWA_BWD_BATCH * 16;
+    constexpr size_t O_HDR = O_PEND + (size_t)EWA_BWD_WARPS * EWA_SLOTS * EWA_SLOT_STRIDE * 4;
+    constexpr size_t O_PIX = O_HDR + (size_t)EWA_BWD_WARPS * EWA_SLOTS * 32;
+    constexpr int PIX_GROUP = EWA_PPL * PIXV + 1;   // float4 per phase-2 lane group; odd spacing keeps the groups' loads in different banks
+    constexpr size_t O_MISC = O_PIX + (size_t)EWA_BWD_WARPS * EWA_LPS * PIX_GROUP * 16;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ewa_smem + O_MISC);
+    int* s_arrive = reinterpret_cast<int*>(full_bar + 8);
+    int* s_maxlast = s_arrive + 8;
 
     const int tile = blockIdx.x / EWA_BWD_SPLIT;
     const int tx = tile % gx, ty = tile / gx;
-    const int warp = (threadIdx.x >> 5) + (blockIdx.x % EWA_BWD_SPLIT) * EWA_BWD_WARPS, lane = threadIdx.x & 31;
+    const int wic = threadIdx.x >> 5;
+    const int warp = wic + (blockIdx.x % EWA_BWD_SPLIT) * EWA_BWD_WARPS, lane = threadIdx.x & 31;
     const int wx0 = (warp & 1) * 8, wy0 = (warp >> 1) * 4;
     const int lx = wx0 + (lane & 7), ly = wy0 + (lane >> 3);
     const int px = tx * TILE + lx, py = ty * TILE + ly;
@@ -298,6 +293,9 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
     const float by0 = (float)wy0 - CULL_MARGIN, by1 = (float)(wy0 + 3) + CULL_MARGIN;
     const size_t N = (size_t)W * H;
     const size_t pid = (size_t)py * W + px;
+    float* pend = reinterpret_cast<float*>(ewa_smem + O_PEND) + (size_t)wic * EWA_SLOTS * EWA_SLOT_STRIDE;
+    float4* hdr = reinterpret_cast<float4*>(ewa_smem + O_HDR) + wic * EWA_SLOTS * 2;
+    float4* pixc = reinterpret_cast<float4*>(ewa_smem + O_PIX) + wic * EWA_LPS * PIX_GROUP;
 
     const uint32_t range_x = tile_offset[tile];
     const int n = (int)(tile_offset[tile + 1] - range_x);
@@ -306,24 +304,27 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
     const int last = inside ? (int)n_contrib[pid] : 0;   // entries [0, last) contribute
     const int wlast = __reduce_max_sync(FULLMASK, last);
     if (threadIdx.x == 0) {
-        s_maxlast = 0;
+        *s_maxlast = 0;
 #pragma unroll
         for (int i = 0; i < EWA_BWD_STAGES; i++) { mbar_init(&full_bar[i], 1); s_arrive[i] = 0; }
         mbar_fence_init();
     }
     __syncthreads();
-    if (lane == 0 && wlast > 0) atomicMax(&s_maxlast, wlast);
+    if (lane == 0 && wlast > 0) atomicMax(s_maxlast, wlast);
     __syncthreads();
-    const int maxlast = min(s_maxlast, n);
+    const int maxlast = min(*s_maxlast, n);
     if (maxlast <= 0) return;
-    const int nb = (maxlast + RBATCH - 1) / RBATCH;
+    const int nb = (maxlast + EWA_BWD_BATCH - 1) / EWA_BWD_BATCH;
 
-    auto batch_count = [&](int b) { return min(RBATCH, n - b * RBATCH); };
+    auto batch_count = [&](int b) { return min(EWA_BWD_BATCH, n - b * EWA_BWD_BATCH); };
+    auto issue = [&](int stage, int b) {
+        const uint32_t bytes = (uint32_t)batch_count(b) * 16u;
+        mbar_expect_tx(&full_bar[stage], bytes * NPL);
+#pragma unroll
+        for (int pl = 0; pl < NPL; pl++) bulk_g2s(&sbuf[stage][pl][0], src + pl * pstride + b * EWA_BWD_BATCH, bytes, &full_bar[stage]);
+    };
     if (threadIdx.x == 0)
-        for (int i = 0; i < EWA_BWD_STAGES && nb - 1 - i >= 0; i++) {
-            const int b = nb - 1 - i;
-            ewa_issue_batch<NPL>(sbuf[i], src, pstride, b * RBATCH, batch_count(b), &full_bar[i]);
-        }
+        for (int i = 0; i < EWA_BWD_STAGES && nb - 1 - i >= 0; i++) issue(i, nb - 1 - i);
 
     const float T_final = inside ? final_T[pid] : 0.f;
     float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f;
@@ -345,22 +346,90 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
             dam2 += dpd * (distance / (tmp * tmp));
         }
     }
-    const float bg_dot_dpixel = __ldg(bg) * dpx0 + __ldg(bg + 1) * dpx1 + __ldg(bg + 2) * dpx2;
-    const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;   // G/backward.cu:460-461
+    const float k_tail = -T_final * (__ldg(bg) * dpx0 + __ldg(bg + 1) * dpx1 + __ldg(bg + 2) * dpx2);   // G/backward.cu:497-500
+    {
+        float4* mine = pixc + (lane / EWA_PPL) * PIX_GROUP + (lane % EWA_PPL) * PIXV;
+        mine[0] = make_float4(dpx0, dpx1, dpx2, dam0);
+        if (GEO) mine[1] = make_float4(dam1, dam2, dam3, dam4);
+    }
+    __syncwarp();
 
-    float T = T_final;
-    float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;
-    float lm0 = 0.f, lm1 = 0.f, lm2 = 0.f, lm3 = 0.f, lm4 = 0.f, am0 = 0.f, am1 = 0.f, am2 = 0.f, am3 = 0.f, am4 = 0.f;
+    // ---- phase 2 ----
+    const int ps = lane % EWA_SLOTS, ph = lane / EWA_SLOTS;
+    const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;     // G/backward.cu:460-461
+    auto flush = [&](int np) {
+        __syncwarp();
+        float s0 = 0.f, sx = 0.f, sy = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f, ax = 0.f, ay = 0.f;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
+        float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+        if (ps < np) {
+            h0 = hdr[ps * 2]; h1 = hdr[ps * 2 + 1];          // (index bits, centre x, centre y, opacity) (conic a, b, c, -)
+            const float X0 = h0.y - (float)wx0, Y0 = h0.z - (float)(wy0 + ph * (EWA_PPL / 8));   // centre in this lane's pixel frame
+            const float* pb = pend + ps * EWA_SLOT_STRIDE + ph * (EWA_PPL * 2);
+            const float4* pk = pixc + ph * PIX_GROUP;
+#pragma unroll
+            for (int i = 0; i < EWA_PPL; i++) {
+                const float2 u = *reinterpret_cast<const float2*>(pb + i * 2);        // v, w
+                const float4 k0 = pk[i * PIXV];
+                const float xi = (float)(i & 7), yi = (float)(i >> 3);
+                s0 += u.x;
+                if ((i & 7) != 0) { sx = fmaf(xi, u.x, sx); sxx = fmaf(xi * xi, u.x, sxx); }
+                if ((i >> 3) != 0) { sy = fmaf(yi, u.x, sy); syy = fmaf(yi * yi, u.x, syy); }
+                if ((i & 7) != 0 && (i >> 3) != 0) sxy = fmaf(xi * yi, u.x, sxy);
+                if (MODE != 0) {                                                      // |dL_dmean2D| per pair (L/backward.cu:602-603)
+                    const float dx = X0 - xi, dy = Y0 - yi, av = fabsf(u.x);
+                    ax = fmaf(av, fabsf(fmaf(dx, h1.x, dy * h1.y)), ax);
+                    ay = fmaf(av, fabsf(fmaf(dy, h1.z, dx * h1.y)), ay);
+                }
+                c0 = fmaf(u.y, k0.x, c0); c1 = fmaf(u.y, k0.y, c1); c2 = fmaf(u.y, k0.z, c2);
+                if (GEO) {
+                    const float4 k1 = pk[i * PIXV + 1];
+                    m0 = fmaf(u.y, k0.w, m0); m1 = fmaf(u.y, k1.x, m1); m2 = fmaf(u.y, k1.y, m2);
+                    m3 = fmaf(u.y, k1.z, m3); m4 = fmaf(u.y, k1.w, m4);
+                }
+            }
+            // moments about the splat centre: d = centre - pixel
+            const float qx = X0 * s0 - sx, qy = Y0 * s0 - sy;
+            const float qxx = fmaf(X0, X0 * s0 - 2.f * sx, sxx), qyy = fmaf(Y0, Y0 * s0 - 2.f * sy, syy);
+            const float qxy = fmaf(X0, Y0 * s0 - sy, fmaf(-Y0, sx, sxy));
+            sx = qx; sy = qy; sxx = qxx; syy = qyy; sxy = qxy;
+        }
+#pragma unroll
+        for (int o = EWA_SLOTS; o < 32; o <<= 1) {
+            s0 += __shfl_xor_sync(FULLMASK, s0, o); sx += __shfl_xor_sync(FULLMASK, sx, o); sy += __shfl_xor_sync(FULLMASK, sy, o);
+            sxx += __shfl_xor_sync(FULLMASK, sxx, o); sxy += __shfl_xor_sync(FULLMASK, sxy, o); syy += __shfl_xor_sync(FULLMASK, syy, o);
+            c0 += __shfl_xor_sync(FULLMASK, c0, o); c1 += __shfl_xor_sync(FULLMASK, c1, o); c2 += __shfl_xor_sync(FULLMASK, c2, o);
+            if (MODE != 0) { ax += __shfl_xor_sync(FULLMASK, ax, o); ay += __shfl_xor_sync(FULLMASK, ay, o); }
+            if (GEO) {
+                m0 += __shfl_xor_sync(FULLMASK, m0, o); m1 += __shfl_xor_sync(FULLMASK, m1, o); m2 += __shfl_xor_sync(FULLMASK, m2, o);
+                m3 += __shfl_xor_sync(FULLMASK, m3, o); m4 += __shfl_xor_sync(FULLMASK, m4, o);
+            }
+        }
+        if (ph == 0 && ps < np) {
+            const float op = h0.w, ca = h1.x, cb = h1.y, cc = h1.z;
+            float* acc = gacc + (size_t)__float_as_uint(h0.x) * EWA_GACC;
+            // dL_dG dG/ddelx = -opacity v (a dx + b dy);  dL_dconic = -0.5 opacity v d d^T
+            const float g0 = -op * (ca * sx + cb * sy) * half_W, g1 = -op * (cc * sy + cb * sx) * half_H;
+            ewa_red_add_v4(acc + 0, g0, g1, -0.5f * op * sxx, -0.5f * op * sxy);
+            ewa_red_add_v4(acc + 4, -0.5f * op * syy, s0, c0, c1);
+            if (MODE == 0) atomicAdd(acc + 8, c2);
+            else ewa_red_add_v4(acc + 8, c2, op * ax * half_W, op * ay * half_H, m0);
+            if (GEO) ewa_red_add_v4(acc + 12, m1, m2, m3, m4);
+        }
+        __syncwarp();
+    };
 
+    float T = T_final, rec = 0.f;
+    int npend = 0;
     int stage = 0;
     uint32_t parity = 0;
     for (int it = 0; it < nb; it++) {
         const int b = nb - 1 - it;
         const int cnt = batch_count(b);
-        const int base = b * RBATCH;
+        const int base = b * EWA_BWD_BATCH;
         mbar_wait(&full_bar[stage], parity);
         if (base < wlast) {
-            const float4(*sb)[RBATCH] = sbuf[stage];
+            const float4(*sb)[EWA_BWD_BATCH] = sbuf[stage];
             for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
                 if (base + c0 >= wlast) continue;
                 const int e = c0 + lane;
@@ -379,55 +448,35 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                     const EwaEval ev = ewa_eval(p0, p1, fx, fy);
                     const bool valid = ev.valid && pos < last;
                     if (!__any_sync(FULLMASK, valid)) continue;
-
                     const float4 pc = sb[2][j];
-                    float v[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = 0.f;
+                    float2 o = make_float2(0.f, 0.f);
                     if (valid) {
-                        const float alpha = ev.alpha, G = ev.G;
+                        const float alpha = ev.alpha;
                         const float ria = fast_rcp(1.0f - alpha);
                         T = T * ria;
-                        const float w = alpha * T;
-                        const float omla = 1.f - last_alpha;
-                        ar0 = last_alpha * lc0 + omla * ar0; lc0 = pc.x;
-                        ar1 = last_alpha * lc1 + omla * ar1; lc1 = pc.y;
-                        ar2 = last_alpha * lc2 + omla * ar2; lc2 = pc.z;
-                        float dL_dalpha = (pc.x - ar0) * dpx0 + (pc.y - ar1) * dpx1 + (pc.z - ar2) * dpx2;
-                        v[6] = w * dpx0; v[7] = w * dpx1; v[8] = w * dpx2;
+                        float S = pc.x * dpx0;
+                        S = fmaf(pc.y, dpx1, S); S = fmaf(pc.z, dpx2, S);
                         if (GEO) {
                             const float4 pm = sb[NPL - 1][j];
-                            am0 = last_alpha * lm0 + omla * am0; lm0 = pm.x;
-                            am1 = last_alpha * lm1 + omla * am1; lm1 = pm.y;
-                            am2 = last_alpha * lm2 + omla * am2; lm2 = pm.z;
-                            am3 = last_alpha * lm3 + omla * am3; lm3 = pm.w;
-                            am4 = last_alpha * lm4 + omla * am4; lm4 = pc.w;
-                            dL_dalpha += (pm.x - am0) * dam0 + (pm.y - am1) * dam1 + (pm.z - am2) * dam2 +
-                                         (pm.w - am3) * dam3 + (pc.w - am4) * dam4;
-                            v[11] = w * dam0; v[12] = w * dam1; v[13] = w * dam2; v[14] = w * dam3; v[15] = w * dam4;
+                            S = fmaf(pm.x, dam0, S); S = fmaf(pm.y, dam1, S); S = fmaf(pm.z, dam2, S);
+                            S = fmaf(pm.w, dam3, S); S = fmaf(pc.w, dam4, S);
                         }
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final * ria) * bg_dot_dpixel;
-                        const float dL_dG = p1.y * dL_dalpha;
-                        const float gdx = G * ev.dx, gdy = G * ev.dy;
-                        const float dG_ddelx = -gdx * p0.z - gdy * p0.w;
-                        const float dG_ddely = -gdy * p1.x - gdx * p0.w;
-                        v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                        v[1] = dL_dG * dG_ddely * ddely_dy;
-                        v[2] = -0.5f * gdx * ev.dx * dL_dG;
-                        v[3] = -0.5f * gdx * ev.dy * dL_dG;
-                        v[4] = -0.5f * gdy * ev.dy * dL_dG;
-                        v[5] = G * dL_dalpha;
-                        if (MODE != 0) { v[9] = fabsf(v[0]); v[10] = fabsf(v[1]); }
+                        const float D = S - rec;
+                        rec = fmaf(alpha, D, rec);
+                        const float dL_dalpha = fmaf(D, T, k_tail * ria);
+                        o = make_float2(ev.G * dL_dalpha, alpha * T);
                     }
-                    const float red = ewa_reduce16(v, lane);
-                    const uint32_t g = __float_as_uint(p1.w) & (USED ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS);
-                    const int vi = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    if ((lane & 1) == 0 && vi < NV) atomicAdd(gacc + (size_t)g * EWA_GACC + vi, red);
+                    *reinterpret_cast<float2*>(pend + npend * EWA_SLOT_STRIDE + lane * 2) = o;
+                    if (lane == 0) {
+                        const uint32_t g = __float_as_uint(p1.w) & (USED ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS);
+                        hdr[npend * 2] = make_float4(__uint_as_float(g), p0.x, p0.y, p1.y);
+                        hdr[npend * 2 + 1] = make_float4(p0.z, p0.w, p1.x, 0.f);
+                    }
+                    if (++npend == EWA_SLOTS) { flush(EWA_SLOTS); npend = 0; }
                 }
             }
         }
+        if (sync_ring) __syncthreads();          // validation only (gsr_set_option("dbg", 2)), see surfel_render_bwd.cu
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
@@ -435,24 +484,43 @@ ewa_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
             if ((old & (EWA_BWD_WARPS - 1)) == EWA_BWD_WARPS - 1 && it + EWA_BWD_STAGES < nb) {
                 __threadfence_block();
                 fence_proxy_async();
-                const int b2 = nb - 1 - (it + EWA_BWD_STAGES);
-                ewa_issue_batch<NPL>(sbuf[stage], src, pstride, b2 * RBATCH, batch_count(b2), &full_bar[stage]);
+                issue(stage, nb - 1 - (it + EWA_BWD_STAGES));
             }
         }
         if (++stage == EWA_BWD_STAGES) { stage = 0; parity ^= 1u; }
     }
+    if (npend) flush(npend);
 }
-template __global__ void ewa_render_bwd<0, false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
-template __global__ void ewa_render_bwd<0, true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
-template __global__ void ewa_render_bwd<1, false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
-template __global__ void ewa_render_bwd<1, true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
-template __global__ void ewa_render_bwd<2, false>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
-template __global__ void ewa_render_bwd<2, true>(const uint32_t*, const float4*, size_t, int, int, int, const float*, float, float,
-    const float*, const uint32_t*, const float*, const float*, const float*, const float*, float*);
+
+template <int MODE, bool USED>
+static cudaError_t ewa_bwd_launch(dim3 grid, cudaStream_t s, const uint32_t* tile_offset, const float4* planes, size_t pstride, int W,
+                                  int H, int gx, const float* bg, float focal_x, float focal_y, const float* final_T,
+                                  const uint32_t* n_contrib, const float* amp, const float* dL_dpix, const float* dam, const float* dpd,
+                                  float* gacc, int sync_ring) {
+    static bool ready[64] = {};          // the opt-in shared-memory size is a per-device function attribute
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !ready[dev]) {
+        e = cudaFuncSetAttribute(ewa_render_bwd<MODE, USED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ewa_bwd_smem<MODE>());
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) ready[dev] = true;
+    }
+    ewa_render_bwd<MODE, USED><<<grid, EWA_BWD_WARPS * 32, ewa_bwd_smem<MODE>(), s>>>(tile_offset, planes, pstride, W, H, gx, bg, focal_x,
+                                                                                     focal_y, final_T, n_contrib, amp, dL_dpix, dam, dpd, gacc, sync_ring);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ewa_render_bwd(int mode, bool used, int ntiles, const uint32_t* tile_offset, const float4* planes, size_t pstride,
+                                  int W, int H, int gx, const float* bg, float focal_x, float focal_y, const float* final_T,
+                                  const uint32_t* n_contrib, const float* amp, const float* dL_dpix, const float* dam, const float* dpd,
+                                  float* gacc, int sync_ring, cudaStream_t s) {
+    const dim3 grid(ntiles * EWA_BWD_SPLIT);
+#define GSR_EWA_BWD(M, U) ewa_bwd_launch<M, U>(grid, s, tile_offset, planes, pstride, W, H, gx, bg, focal_x, focal_y, final_T, n_contrib, amp, dL_dpix, dam, dpd, gacc, sync_ring)
+    if (mode == 2) return used ? GSR_EWA_BWD(2, true) : GSR_EWA_BWD(2, false);
+    if (mode == 1) return used ? GSR_EWA_BWD(1, true) : GSR_EWA_BWD(1, false);
+    return used ? GSR_EWA_BWD(0, true) : GSR_EWA_BWD(0, false);
+#undef GSR_EWA_BWD
+}
 
 }  // namespace gsr

@@ -79,7 +79,11 @@ static_assert(BWD_WARPS == 2 || BWD_WARPS == 4 || BWD_WARPS == 8, "warps per CTA
 constexpr size_t SM_RING = (size_t)BWD_STAGES * REC_PLANES * BWD_BATCH * 16;
 constexpr size_t SM_PEND = (size_t)BWD_WARPS * BWD_SLOTS * SLOT_STRIDE * 4;
 constexpr size_t SM_HDR = (size_t)BWD_WARPS * BWD_SLOTS * 16;
-constexpr size_t SM_PIXC = (size_t)BWD_WARPS * 32 * 3 * 16;   // per pixel: (dpx0 dpx1 dpx2 dn0) (dn1 dn2 - -) (dmn0 dmn1 dmn2 -)
+// per pixel: (dpx0 dpx1 dpx2 dn0) (dn1 dn2 - -) (dmn0 dmn1 dmn2 -).  The pixels of one phase-2 lane group are contiguous and
+// the groups are spaced an odd number of float4 apart: the BWD_LPS addresses one phase-2 load touches then fall into
+// different banks (with a multiple of 128 B between them every such load was a BWD_LPS-way conflict: 8 wavefronts / pair).
+constexpr int PIXC_GROUP = BWD_PPL * 3 + 1;
+constexpr size_t SM_PIXC = (size_t)BWD_WARPS * BWD_LPS * PIXC_GROUP * 16;
 constexpr size_t SM_MISC = 128;
 constexpr size_t BWD_SMEM = SM_RING + SM_PEND + SM_HDR + SM_PIXC + SM_MISC;
 constexpr int BWD_MAXB = (int)((227 * 1024) / (BWD_SMEM + 1024));
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, BWD_MINB)
 surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, const float* __restrict__ final_T,
                   const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
-                  const float* __restrict__ dL_dothers, float* __restrict__ gacc) {
+                  const float* __restrict__ dL_dothers, float* __restrict__ gacc, int sync_ring) {
     // BWD_STAGES-deep ring of record batches.  Warps are NOT synchronised per batch: every warp waits on the
     // stage's full barrier, consumes (or skips) the batch and then arrives on the stage's counter; the warp whose
     // arrival is the last re-arms the barrier and issues the bulk copy of the batch BWD_STAGES ahead into the freed
@@ -124,7 +128,7 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     const size_t pid = (size_t)py * W + px;
     float* pend = pend_all + (size_t)wic * BWD_SLOTS * SLOT_STRIDE;
     float4* hdr = hdr_all + wic * BWD_SLOTS;
-    float4* pixc = pixc_all + wic * 32 * 3;
+    float4* pixc = pixc_all + wic * BWD_LPS * PIXC_GROUP;
 
     const uint32_t range_x = tile_offset[tile];
     const int n = (int)(tile_offset[tile + 1] - range_x);
@@ -174,9 +178,12 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     const float m2fD = -2.0f * final_D;
     const float reg2 = 2.0f * dL_dreg;
     // phase 2 reads the upstream gradients of all 32 pixels of the block
-    pixc[lane * 3 + 0] = make_float4(dpx0, dpx1, dpx2, dn0);
-    pixc[lane * 3 + 1] = make_float4(dn1, dn2, 0.f, 0.f);
-    pixc[lane * 3 + 2] = make_float4(dmn0, dmn1, dmn2, 0.f);
+    {
+        float4* mine = pixc + (lane / BWD_PPL) * PIXC_GROUP + (lane % BWD_PPL) * 3;
+        mine[0] = make_float4(dpx0, dpx1, dpx2, dn0);
+        mine[1] = make_float4(dn1, dn2, 0.f, 0.f);
+        mine[2] = make_float4(dmn0, dmn1, dmn2, 0.f);
+    }
     const bool has_dmn = __any_sync(FULLMASK, dmn0 != 0.f || dmn1 != 0.f || dmn2 != 0.f);   // quirk Q1; never set by GS-SR
     __syncwarp();
 
@@ -188,7 +195,7 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
         float c0 = 0.f, c1 = 0.f, c2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, so = 0.f;
         if (ps < np) {
             const float* pb = pend + ps * SLOT_STRIDE + ph * (BWD_PPL * PAIR_VALS);
-            const float4* pk = pixc + ph * (BWD_PPL * 3);
+            const float4* pk = pixc + ph * PIXC_GROUP;
 #pragma unroll
             for (int i = 0; i < BWD_PPL; i++) {
                 const float2 u0 = *reinterpret_cast<const float2*>(pb + i * PAIR_VALS);
@@ -334,7 +341,10 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 }
             }
         }
-        // release the stage; the last of the CTA's warps to arrive refills it with the batch BWD_STAGES ahead
+        // release the stage; the last of the CTA's warps to arrive refills it with the batch BWD_STAGES ahead.
+        // sync_ring (validation only, gsr_set_option("dbg", 2)): a CTA barrier per batch makes the refill trivially ordered
+        // after every warp's reads -- the reference point the decoupled handshake is stress-tested against.
+        if (sync_ring) __syncthreads();
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
@@ -353,7 +363,7 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
 
 cudaError_t launch_surfel_render_bwd(bool used, int ntiles, const uint32_t* tile_offset, const float4* planes, size_t pstride,
                                      int W, int H, int gx, const float* bg, const float* final_T, const uint32_t* n_contrib,
-                                     const float* dL_dpix, const float* dL_dothers, float* gacc, cudaStream_t s) {
+                                     const float* dL_dpix, const float* dL_dothers, float* gacc, int sync_ring, cudaStream_t s) {
     // the opt-in shared-memory size is a per-device function attribute
     static bool ready[64] = {};
     int dev = 0;
@@ -369,10 +379,10 @@ cudaError_t launch_surfel_render_bwd(bool used, int ntiles, const uint32_t* tile
     const dim3 grid(ntiles * BWD_SPLIT), block(BWD_WARPS * 32);
     if (used)
         surfel_render_bwd<true><<<grid, block, BWD_SMEM, s>>>(tile_offset, planes, pstride, W, H, gx, bg, final_T, n_contrib, dL_dpix,
-                                                               dL_dothers, gacc);
+                                                               dL_dothers, gacc, sync_ring);
     else
         surfel_render_bwd<false><<<grid, block, BWD_SMEM, s>>>(tile_offset, planes, pstride, W, H, gx, bg, final_T, n_contrib, dL_dpix,
-                                                                dL_dothers, gacc);
+                                                                dL_dothers, gacc, sync_ring);
     return cudaGetLastError();
 }
 
