@@ -141,7 +141,11 @@ def pipelined_e2e(step_fn, host, template, out_host, steps, barrier):
     import torch
     cur = torch.cuda.current_stream()
     h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
-    staged = [{k: torch.empty_like(v) for k, v in template.items()} for _ in range(2)]
+    # one packed device buffer per stage (views per tensor): the step's inputs travel as ONE cudaMemcpyAsync from the
+    # packed pinned host buffer instead of one copy per tensor
+    packed_host = host["_packed"]
+    staged_packed = [torch.empty(packed_host.shape, dtype=packed_host.dtype, device=cur.device) for _ in range(2)]
+    staged = [unpack_views(sp, host["_layout"]) for sp in staged_packed]
     outs = [torch.empty(out_host.shape, dtype=out_host.dtype, device=cur.device) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -153,8 +157,7 @@ def pipelined_e2e(step_fn, host, template, out_host, steps, barrier):
         with torch.cuda.stream(h2d):
             if i >= 2:
                 h2d.wait_event(consumed[b])
-            for k in staged[b]:
-                staged[b][k].copy_(host[k], non_blocking=True)
+            staged_packed[b].copy_(packed_host, non_blocking=True)
             ready[b].record(h2d)
 
     barrier()
@@ -183,14 +186,71 @@ def pipelined_e2e(step_fn, host, template, out_host, steps, barrier):
     return e0.elapsed_time(e1)
 
 
+def unpack_views(packed, layout):
+    """{name: view} of one packed float32 buffer; layout = [(name, offset, shape)]."""
+    out = {}
+    for name, off, shape in layout:
+        n = int(np.prod(shape))
+        out[name] = packed[off: off + n].view(shape)
+    return out
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated: pages
+    are placed on the allocating thread's node (first touch), so every rank's per-step upload then reads local DRAM
+    instead of crossing the socket interconnect.  Under torchrun the ranks are otherwise unbound.  Returns the node or None."""
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "none reported (single-node host)"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
+def h2d_copy_only_gbs(host, device, barrier, reps=20):
+    """Bandwidth of the packed upload alone (all ranks at once): what the host link / host DRAM can feed this rank."""
+    import torch
+    dst = torch.empty(host["_packed"].shape, dtype=host["_packed"].dtype, device=device)
+    for _ in range(3):
+        dst.copy_(host["_packed"], non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(host["_packed"], non_blocking=True)
+    e1.record()
+    barrier()
+    return host["_packed"].numel() * 4 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def build_inputs(P, W, H, seed, device):
     import torch
     import synth
     sc = synth.make_scene(P, W, H, seed=seed)
     gc, go = synth.make_upstream_grads(W, H, seed=seed + 1)
-    host = {k: torch.from_numpy(np.ascontiguousarray(getattr(sc, k))).pin_memory()
-            for k in ("means3D", "scales", "rotations", "opacities", "colors")}
+    names = ("means3D", "scales", "rotations", "opacities", "colors")
+    arrays = {k: np.ascontiguousarray(getattr(sc, k), dtype=np.float32) for k in names}
+    layout, off = [], 0
+    for k in names:
+        layout.append((k, off, tuple(arrays[k].shape)))
+        off += (arrays[k].size + 63) // 64 * 64                     # keep every tensor 256-byte aligned
+    packed = torch.empty(off, dtype=torch.float32).pin_memory()
+    host = unpack_views(packed, layout)
+    for k in names:
+        host[k].copy_(torch.from_numpy(arrays[k]))
     dev = {k: v.to(device) for k, v in host.items()}
+    host["_packed"], host["_layout"] = packed, layout
     cam = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in
            dict(bg=sc.cam.bg, view=sc.cam.viewmatrix, proj=sc.cam.projmatrix, campos=sc.cam.campos).items()}
     g = (torch.from_numpy(gc).to(device), torch.from_numpy(go).to(device))
@@ -249,8 +309,9 @@ def run_ours(args, rank, world, device):
     pipelined_e2e(step, host, dev, out_host, 2, barrier)  # warm the side streams / allocator
     ms_e2e = shard.max_over_ranks(pipelined_e2e(step, host, dev, out_host, args.steps, barrier), device)
     clocks = sampler.stop() if rank == 0 else None
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = host["_packed"].numel() * 4
     d2h = out_host.numel() * out_host.element_size()
+    copy_gbs = h2d_copy_only_gbs(host, device, barrier)
 
     # per-kernel durations (cudaEvents inside the library, outside the timed regions)
     L = gsr_b200.lib()
@@ -267,7 +328,7 @@ def run_ours(args, rank, world, device):
     kernel_ms = {n: float(acc[i] / nprof) for i, n in enumerate(PROF_NAMES)}
     V = int((state["radii"] > 0).sum().item())
     return dict(ms_resident=ms_resident, ms_e2e=ms_e2e, clocks=clocks, h2d=h2d, d2h=d2h, kernel_ms=kernel_ms, V=V,
-                sc=sc, checksum=float(state["color"].double().sum().item()), step_ms=step_ms)
+                sc=sc, checksum=float(state["color"].double().sum().item()), step_ms=step_ms, copy_gbs=copy_gbs)
 
 
 def run_reference_cuda(args, rank, world, device):
@@ -306,9 +367,9 @@ def run_reference_cuda(args, rank, world, device):
     out_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
     pipelined_e2e(step, host, dev, out_host, 2, barrier)
     ms_e2e = shard.max_over_ranks(pipelined_e2e(step, host, dev, out_host, args.steps, barrier), device)
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = host["_packed"].numel() * 4
     return dict(ms_resident=ms_resident, ms_e2e=ms_e2e, h2d=h2d, d2h=out_host.numel() * 4, R=int(state["R"]),
-                V=int((state["radii"] > 0).sum().item()), step_ms=step_ms)
+                V=int((state["radii"] > 0).sum().item()), step_ms=step_ms, copy_gbs=h2d_copy_only_gbs(host, device, barrier))
 
 
 def step_stats(step_ms):
@@ -394,6 +455,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=device)
@@ -413,7 +475,8 @@ def main():
                 ve = args.P * world * args.steps / (r["ms_e2e"] * 1e-3)
                 base.update({"impl": "reference", "value": v, "ms_per_step": r["ms_resident"] / args.steps,
                              "e2e": {"value": ve, "unit": "Gaussians/s", "h2d_bytes_per_step": r["h2d"],
-                                     "d2h_bytes_per_step": r["d2h"]},
+                                     "d2h_bytes_per_step": r["d2h"], "numa_node": numa_node,
+                                     "h2d_copy_only_gbs_rank0": r["copy_gbs"]},
                              "cpu_baseline": {"value": v, "unit": "Gaussians/s", "cores": 0, "kind": "reference",
                                               "sample": "the reference has no CPU path: its own UNMODIFIED CUDA "
                                                         "kernels (diff-surfel-rasterization compiled for sm_100a "
@@ -453,7 +516,9 @@ def main():
         achieved = ab[dom] / (r["kernel_ms"][dom] * 1e-3) / 1e9
         base.update({
             "value": v, "ms_per_step": r["ms_resident"] / args.steps,
-            "e2e": {"value": ve, "unit": "Gaussians/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "e2e": {"value": ve, "unit": "Gaussians/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "numa_node": numa_node, "h2d_copy_only_gbs_rank0": r["copy_gbs"],
+                    "upload": "one packed pinned buffer per step (1 cudaMemcpyAsync), process bound to the GPU's NUMA node"},
             "gpu_launches": OWN_KERNELS_PER_STEP * args.steps,
             "clocks": r["clocks"],
             "roofline": {"bound": "hbm", "kernel": f"gsr::surfel_{dom}", "achieved": achieved, "peak": peak,

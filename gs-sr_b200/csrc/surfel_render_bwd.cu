@@ -55,7 +55,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 #define GSR_BWD_BATCH 32
 #endif
 #ifndef GSR_BWD_STAGES
-#define GSR_BWD_STAGES 4
+#define GSR_BWD_STAGES 5
 #endif
 #ifndef GSR_BWD_WARPS
 #define GSR_BWD_WARPS 8
@@ -79,10 +79,11 @@ static_assert(BWD_WARPS == 2 || BWD_WARPS == 4 || BWD_WARPS == 8, "warps per CTA
 constexpr size_t SM_RING = (size_t)BWD_STAGES * REC_PLANES * BWD_BATCH * 16;
 constexpr size_t SM_PEND = (size_t)BWD_WARPS * BWD_SLOTS * SLOT_STRIDE * 4;
 constexpr size_t SM_HDR = (size_t)BWD_WARPS * BWD_SLOTS * 16;
-// per pixel: (dpx0 dpx1 dpx2 dn0) (dn1 dn2 - -) (dmn0 dmn1 dmn2 -).  The pixels of one phase-2 lane group are contiguous and
+// per pixel: (dpx0 dpx1 dpx2 dn0) (dn1 dn2 - -); the median-normal gradients (quirk Q1, never set by GS-SR) are re-read from
+// global memory in the rare path that needs them.  The pixels of one phase-2 lane group are contiguous and
 // the groups are spaced an odd number of float4 apart: the BWD_LPS addresses one phase-2 load touches then fall into
 // different banks (with a multiple of 128 B between them every such load was a BWD_LPS-way conflict: 8 wavefronts / pair).
-constexpr int PIXC_GROUP = BWD_PPL * 3 + 1;
+constexpr int PIXC_GROUP = BWD_PPL * 2 + 1;
 constexpr size_t SM_PIXC = (size_t)BWD_WARPS * BWD_LPS * PIXC_GROUP * 16;
 constexpr size_t SM_MISC = 128;
 constexpr size_t BWD_SMEM = SM_RING + SM_PEND + SM_HDR + SM_PIXC + SM_MISC;
@@ -179,10 +180,9 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     const float reg2 = 2.0f * dL_dreg;
     // phase 2 reads the upstream gradients of all 32 pixels of the block
     {
-        float4* mine = pixc + (lane / BWD_PPL) * PIXC_GROUP + (lane % BWD_PPL) * 3;
+        float4* mine = pixc + (lane / BWD_PPL) * PIXC_GROUP + (lane % BWD_PPL) * 2;
         mine[0] = make_float4(dpx0, dpx1, dpx2, dn0);
         mine[1] = make_float4(dn1, dn2, 0.f, 0.f);
-        mine[2] = make_float4(dmn0, dmn1, dmn2, 0.f);
     }
     const bool has_dmn = __any_sync(FULLMASK, dmn0 != 0.f || dmn1 != 0.f || dmn2 != 0.f);   // quirk Q1; never set by GS-SR
     __syncwarp();
@@ -201,7 +201,7 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 const float2 u0 = *reinterpret_cast<const float2*>(pb + i * PAIR_VALS);
                 const float2 u1 = *reinterpret_cast<const float2*>(pb + i * PAIR_VALS + 2);
                 const float2 u2 = *reinterpret_cast<const float2*>(pb + i * PAIR_VALS + 4);
-                const float4 k0 = pk[i * 3], k1 = pk[i * 3 + 1];
+                const float4 k0 = pk[i * 2], k1 = pk[i * 2 + 1];
                 m0 += u0.x; m1 += u0.y; m2 += u1.x;
                 if ((i & 7) != 0) {
                     const float xi = (float)(i & 7);
@@ -217,11 +217,14 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 so += u2.y;
             }
             if (has_dmn) {
+                // S/backward.cu:381 adds dL/dmedian_normal to EVERY contributing splat; pixel i of this lane's run:
+                const int p0 = ph * BWD_PPL;
 #pragma unroll 4
                 for (int i = 0; i < BWD_PPL; i++)
                     if (pb[i * PAIR_VALS + 4] > 0.f) {       // w > 0 <=> the pair contributed
-                        const float4 k2 = pk[i * 3 + 2];
-                        n0 += k2.x; n1 += k2.y; n2 += k2.z;
+                        const int qx = tx * TILE + wx0 + ((p0 + i) & 7), qy = ty * TILE + wy0 + ((p0 + i) >> 3);
+                        const size_t q = (size_t)qy * W + qx;
+                        n0 += __ldg(dL_dothers + q + 8 * N); n1 += __ldg(dL_dothers + q + 9 * N); n2 += __ldg(dL_dothers + q + 10 * N);
                     }
             }
             // block-local pixel offsets -> offsets from the splat's moment origin (hdr.y, hdr.z; tile-local)

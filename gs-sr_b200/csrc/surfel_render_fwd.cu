@@ -73,9 +73,7 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     float T = 1.0f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
     float Dacc = 0.f, M1 = 0.f, M2 = 0.f, dist = 0.f;
-    float med_depth = 0.f, mn0 = 0.f, mn1 = 0.f, mn2 = 0.f;
-    int surf_idx = -1;
-    uint32_t last_contrib = 0, med_contrib = 0;
+    uint32_t last_contrib = 0, med_contrib = 0;   // median depth / index / normal are re-derived from med_contrib after the walk
     bool done = !inside;
     bool warp_done = __all_sync(FULLMASK, done);
 
@@ -113,20 +111,16 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                             M1 += mm * w;
                             M2 += mm * mm * w;
                             const uint32_t pos = (uint32_t)(b * RBATCH + j + 1);
-                            if (T > 0.5f) {
-                                med_depth = ev.depth;
-                                surf_idx = (int)(__float_as_uint(qd.w) & idx_mask);
-                                mn0 = pn.x; mn1 = pn.y; mn2 = pn.z;
-                                med_contrib = pos;
-                            }
+                            if (T > 0.5f) med_contrib = pos;          // S/forward.cu:402-408: the last splat blended while T > 0.5
                             N0 += pn.x * w; N1 += pn.y * w; N2 += pn.z * w;
                             C0 += pn.w * w; C1 += pc.x * w; C2 += pc.y * w;
                             T = test_T;
                             last_contrib = pos;
                         }
-                        if (__all_sync(FULLMASK, done)) { warp_done = true; break; }
                     }
                 }
+                // checked once per 32-entry chunk: after the last pixel finishes, the rest of the chunk only evaluates
+                if (__all_sync(FULLMASK, done)) warp_done = true;
                 // hand the contributing entries to the backward: one predicated red.or per chunk into the record word
                 if (MARK && ((used >> lane) & 1u))
                     atomicOr(reinterpret_cast<uint32_t*>(mark_plane + range_x + b * RBATCH + c0 + lane) + 3,
@@ -150,6 +144,18 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
         const float bg0 = __ldg(bg), bg1 = __ldg(bg + 1), bg2 = __ldg(bg + 2);
         const size_t N = (size_t)W * H;
         const size_t pid = (size_t)py * W + px;
+        // median splat: one record read and one re-evaluation per pixel (identical arithmetic, hence identical depth)
+        // instead of six predicated moves per blended pair
+        float med_depth = 0.f, mn0 = 0.f, mn1 = 0.f, mn2 = 0.f;
+        int surf_idx = -1;
+        if (med_contrib > 0) {
+            const float4* rec = src + (med_contrib - 1);
+            const float4 qa = __ldg(rec), qb = __ldg(rec + pstride), qc = __ldg(rec + 2 * pstride), qd = __ldg(rec + 3 * pstride),
+                         pn = __ldg(rec + 4 * pstride);
+            med_depth = eval_pair(qa, qb, qc, qd, fx, fy).depth;
+            surf_idx = (int)(__float_as_uint(qd.w) & idx_mask);
+            mn0 = pn.x; mn1 = pn.y; mn2 = pn.z;
+        }
         final_T[pid] = T;
         final_T[pid + N] = M1;
         final_T[pid + 2 * N] = M2;
