@@ -312,6 +312,7 @@ def run_ours(args, rank, world, device):
     h2d = host["_packed"].numel() * 4
     d2h = out_host.numel() * out_host.element_size()
     copy_gbs = h2d_copy_only_gbs(host, device, barrier)
+    copy_all = [round(m["gbs"], 2) for m in shard.gather_metrics({"gbs": copy_gbs})] if world > 1 else [round(copy_gbs, 2)]
 
     # per-kernel durations (cudaEvents inside the library, outside the timed regions)
     L = gsr_b200.lib()
@@ -328,7 +329,7 @@ def run_ours(args, rank, world, device):
     kernel_ms = {n: float(acc[i] / nprof) for i, n in enumerate(PROF_NAMES)}
     V = int((state["radii"] > 0).sum().item())
     return dict(ms_resident=ms_resident, ms_e2e=ms_e2e, clocks=clocks, h2d=h2d, d2h=d2h, kernel_ms=kernel_ms, V=V,
-                sc=sc, checksum=float(state["color"].double().sum().item()), step_ms=step_ms, copy_gbs=copy_gbs)
+                sc=sc, checksum=float(state["color"].double().sum().item()), step_ms=step_ms, copy_gbs=copy_gbs, copy_all=copy_all)
 
 
 def run_reference_cuda(args, rank, world, device):
@@ -402,6 +403,36 @@ def cpu_oracle_full(P, W, H, stride=4):
                 sample=f"oracle/liborc.so (OpenMP, {os.cpu_count()} threads) on the full workload once: forward+backward of "
                        f"the {P}-surfel scene, every tile, {t_full:.1f}s (preprocess+binning {t_bin:.1f}s of it); the every-"
                        f"{stride}th-tile sample of round 1 extrapolates to {est:.1f}s ({P / est:.0f} Gaussians/s)")
+
+
+def mesh_gather_check(rank, world, device):
+    """Config 5's one collective (extract_mesh_split.py:58-119): every rank fuses ITS tile's views into the same bounded
+    TSDF lattice, the partial volumes are summed onto rank 0 with one NCCL reduce (gsr_b200.tsdf.BoundedTSDFVolume), and
+    rank 0 checks the result against fusing all ranks' views itself.  Returns the record on rank 0, None elsewhere."""
+    import torch
+    from gsr_b200.tsdf import BoundedTSDFVolume
+    from tsdf_synth import build_tsdf_case
+    c = build_tsdf_case("world_rgb", n=8)
+    nv = len(c["projs"])
+    grid = dict(origin=(-0.8, -0.8, -0.8), voxel_size=1.6 / 127, dims=(128, 128, 128), sdf_trunc=0.06, depth_trunc=5.0)
+    pick = lambda idx: ([torch.from_numpy(c["projs"][i]) for i in idx], [torch.from_numpy(c["depthmaps"][i]) for i in idx],  # noqa: E731
+                        [torch.from_numpy(c["rgbmaps"][i]) for i in idx])
+    mine = [(2 * rank) % nv, (2 * rank + 1) % nv]                      # two views per tile
+    vol = BoundedTSDFVolume(with_rgb=True, device=device, **grid).integrate(*pick(mine))
+    warm = torch.zeros(1 << 20, device=device)
+    torch.distributed.reduce(warm, 0)                                  # NCCL channel set-up is not part of the gather
+    torch.distributed.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    vol.reduce_to(0)
+    e1.record(); torch.cuda.synchronize()
+    if rank != 0:
+        return None
+    every = [v for r in range(world) for v in ((2 * r) % nv, (2 * r + 1) % nv)]
+    full = BoundedTSDFVolume(with_rgb=True, device=device, **grid).integrate(*pick(every))
+    return {"voxels": 128 ** 3, "views": len(every), "reduce_ms": e0.elapsed_time(e1), "bytes_per_rank": 128 ** 3 * 20,
+            "max_abs_err_tsdf": float((vol.tsdf - full.tsdf).abs().max()), "weights_equal": bool(torch.equal(vol.weight, full.weight)),
+            "max_abs_err_rgb": float((vol.rgb - full.rgb).abs().max())}
 
 
 def train_iters(impl):
@@ -503,6 +534,7 @@ def main():
         return
 
     r = run_ours(args, rank, world, device)
+    gather = mesh_gather_check(rank, world, device) if world > 1 else None
     if rank == 0:
         v = args.P * world * args.steps / (r["ms_resident"] * 1e-3)
         ve = args.P * world * args.steps / (r["ms_e2e"] * 1e-3)
@@ -518,6 +550,8 @@ def main():
             "value": v, "ms_per_step": r["ms_resident"] / args.steps,
             "e2e": {"value": ve, "unit": "Gaussians/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "numa_node": numa_node, "h2d_copy_only_gbs_rank0": r["copy_gbs"],
+                    "h2d_copy_only_gbs_per_rank": r["copy_all"],   # all ranks uploading at once, nothing else running: the host-link ceiling
+                    "h2d_needed_gbs_per_rank": r["h2d"] / (r["ms_resident"] / args.steps * 1e-3) / 1e9,
                     "upload": "one packed pinned buffer per step (1 cudaMemcpyAsync), process bound to the GPU's NUMA node"},
             "gpu_launches": OWN_KERNELS_PER_STEP * args.steps,
             "clocks": r["clocks"],
@@ -527,7 +561,7 @@ def main():
                          "whole_step_frac": ab["whole_step"] / (r["ms_resident"] / args.steps * 1e-3) / 1e9 / peak,
                          "side_bound": issue_side_bound(dom, r["kernel_ms"][dom], (r["clocks"] or {}).get("sm_mhz"),
                                                         (args.P, args.W, args.H) == (P_DEFAULT, W_DEFAULT, H_DEFAULT))},
-            "kernel_ms": r["kernel_ms"], "step_ms": step_stats(r["step_ms"]),
+            "kernel_ms": r["kernel_ms"], "step_ms": step_stats(r["step_ms"]), "mesh_gather": gather,
             "stats": {"num_rendered": R, "visible": r["V"], "pixels": N, "checksum": r["checksum"]},
         })
         if world == 1 and not args.no_train:
