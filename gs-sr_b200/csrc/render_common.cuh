@@ -24,6 +24,63 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return r;
 }
 
+// Packed FP32 pairs (PTX *.f32x2, SASS FFMA2 / FMUL2 / FADD2 on sm_100a): one issue slot for two IEEE round-to-nearest
+// operations, each half bit-identical to the scalar fmaf / mul / add.  The render kernels are issue-bound (75-83 % of the
+// issue slots, FMA pipe < 40 % busy), so halving the instruction count of the two-wide pieces is what counts.  The
+// (x, y) / (z, w) halves of a 128-bit shared-memory load are already aligned register pairs; a scalar second operand
+// uses the instruction's broadcast form (no MOV).  GSR_FFMA2=0 builds the scalar sequences for A/B runs.
+#ifndef GSR_FFMA2
+#define GSR_FFMA2 1
+#endif
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+#if GSR_FFMA2
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+#if GSR_FFMA2
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+#if GSR_FFMA2
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__device__ __forceinline__ float2 ffma2s(float2 a, float s, float2 c) { return ffma2(a, make_float2(s, s), c); }
+__device__ __forceinline__ float2 fmul2s(float2 a, float s) { return fmul2(a, make_float2(s, s)); }
+
 // One thread: arm the stage's mbarrier and launch the six plane copies of entries
 // [first, first+count) of this tile's list.
 template <int NB>
@@ -57,12 +114,12 @@ struct PairEval {
 // Follows S/forward.cu:351-383 with p = a x + b y + c and depth = det(T)/p.z.
 __device__ __forceinline__ PairEval eval_pair(float4 qa, float4 qb, float4 qc, float4 qd, float fx, float fy) {
     PairEval e;
-    const float p0 = fmaf(qa.x, fx, fmaf(qb.x, fy, qc.x));
-    const float p1 = fmaf(qa.y, fx, fmaf(qb.y, fy, qc.y));
+    const float2 p01 = ffma2s(make_float2(qa.x, qa.y), fx, ffma2s(make_float2(qb.x, qb.y), fy, make_float2(qc.x, qc.y)));
     const float p2 = fmaf(qa.z, fx, fmaf(qb.z, fy, qc.z));
     e.ip = fast_rcp(p2);
-    e.s0 = p0 * e.ip;
-    e.s1 = p1 * e.ip;
+    const float2 s01 = fmul2s(p01, e.ip);
+    e.s0 = s01.x;
+    e.s1 = s01.y;
     const float rho3d = e.s0 * e.s0 + e.s1 * e.s1;
     e.d0 = qa.w - fx;
     e.d1 = qb.w - fy;

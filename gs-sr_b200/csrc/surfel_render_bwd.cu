@@ -176,8 +176,11 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     }
     // alpha channel + background (S/backward.cu:372-376,391-394): (1 - accum_alpha_rec) T_i == T_final / (1 - alpha_i)
     const float k_tail = T_final * (dL_daccum - (__ldg(bg) * dpx0 + __ldg(bg + 1) * dpx1 + __ldg(bg + 2) * dpx2));
-    const float m2fD = -2.0f * final_D;
-    const float reg2 = 2.0f * dL_dreg;
+    // distortion terms (S/backward.cu:347-364) with the upstream weight folded into the three per-pixel constants:
+    //   dL/dweight = (m^2 A - 2 m D + D2) dL_dreg = m (m rA + rB) + rC,   2 (m A - D) dL_dreg = (m + m) rA + rB
+    const float rA = final_A * dL_dreg, rB = -2.0f * final_D * dL_dreg, rC = final_D2 * dL_dreg;
+    // upstream gradients paired against the record halves (normal.xy | normal.z, colour.r | colour.gb)
+    const float2 k_dn01 = make_float2(dn0, dn1), k_dn2px0 = make_float2(dn2, dpx0), k_px12 = make_float2(dpx1, dpx2);
     // phase 2 reads the upstream gradients of all 32 pixels of the block
     {
         float4* mine = pixc + (lane / BWD_PPL) * PIXC_GROUP + (lane % BWD_PPL) * 2;
@@ -191,8 +194,11 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
     const int ps = lane % BWD_SLOTS, ph = lane / BWD_SLOTS;
     auto flush = [&](int np) {
         __syncwarp();
-        float m0 = 0.f, m1 = 0.f, m2 = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f, y0 = 0.f, y1 = 0.f, y2 = 0.f, qs = 0.f;
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, so = 0.f;
+        // accumulators paired for the packed adds / FMAs: the slot's three 64-bit words (a0 a1 | a2 q | w v) and the
+        // halves of the pixels' upstream-gradient words are the operands as they come out of shared memory
+        const float2 z2 = make_float2(0.f, 0.f);
+        float2 m01 = z2, m2q = z2, x01 = z2, y01 = z2, c01 = z2, c2n0 = z2, n12 = z2;
+        float x2 = 0.f, y2 = 0.f, so = 0.f;
         if (ps < np) {
             const float* pb = pend + ps * SLOT_STRIDE + ph * (BWD_PPL * PAIR_VALS);
             const float4* pk = pixc + ph * PIXC_GROUP;
@@ -202,18 +208,19 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 const float2 u1 = *reinterpret_cast<const float2*>(pb + i * PAIR_VALS + 2);
                 const float2 u2 = *reinterpret_cast<const float2*>(pb + i * PAIR_VALS + 4);
                 const float4 k0 = pk[i * 2], k1 = pk[i * 2 + 1];
-                m0 += u0.x; m1 += u0.y; m2 += u1.x;
+                m01 = fadd2(m01, u0);
+                m2q = fadd2(m2q, u1);
                 if ((i & 7) != 0) {
                     const float xi = (float)(i & 7);
-                    x0 = fmaf(xi, u0.x, x0); x1 = fmaf(xi, u0.y, x1); x2 = fmaf(xi, u1.x, x2);
+                    x01 = ffma2s(u0, xi, x01); x2 = fmaf(xi, u1.x, x2);
                 }
                 if ((i >> 3) != 0) {
                     const float yi = (float)(i >> 3);
-                    y0 = fmaf(yi, u0.x, y0); y1 = fmaf(yi, u0.y, y1); y2 = fmaf(yi, u1.x, y2);
+                    y01 = ffma2s(u0, yi, y01); y2 = fmaf(yi, u1.x, y2);
                 }
-                qs += u1.y;
-                c0 = fmaf(u2.x, k0.x, c0); c1 = fmaf(u2.x, k0.y, c1); c2 = fmaf(u2.x, k0.z, c2);
-                n0 = fmaf(u2.x, k0.w, n0); n1 = fmaf(u2.x, k1.x, n1); n2 = fmaf(u2.x, k1.y, n2);
+                c01 = ffma2s(make_float2(k0.x, k0.y), u2.x, c01);
+                c2n0 = ffma2s(make_float2(k0.z, k0.w), u2.x, c2n0);
+                n12 = ffma2s(make_float2(k1.x, k1.y), u2.x, n12);
                 so += u2.y;
             }
             if (has_dmn) {
@@ -224,25 +231,31 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                     if (pb[i * PAIR_VALS + 4] > 0.f) {       // w > 0 <=> the pair contributed
                         const int qx = tx * TILE + wx0 + ((p0 + i) & 7), qy = ty * TILE + wy0 + ((p0 + i) >> 3);
                         const size_t q = (size_t)qy * W + qx;
-                        n0 += __ldg(dL_dothers + q + 8 * N); n1 += __ldg(dL_dothers + q + 9 * N); n2 += __ldg(dL_dothers + q + 10 * N);
+                        c2n0.y += __ldg(dL_dothers + q + 8 * N);
+                        n12.x += __ldg(dL_dothers + q + 9 * N); n12.y += __ldg(dL_dothers + q + 10 * N);
                     }
             }
             // block-local pixel offsets -> offsets from the splat's moment origin (hdr.y, hdr.z; tile-local)
             const float4 h4 = hdr[ps];
             const float ox = (float)wx0 - h4.y, oy = (float)(wy0 + ph * (BWD_PPL / 8)) - h4.z;
-            x0 = fmaf(ox, m0, x0); x1 = fmaf(ox, m1, x1); x2 = fmaf(ox, m2, x2);
-            y0 = fmaf(oy, m0, y0); y1 = fmaf(oy, m1, y1); y2 = fmaf(oy, m2, y2);
+            x01 = ffma2s(m01, ox, x01); x2 = fmaf(ox, m2q.x, x2);
+            y01 = ffma2s(m01, oy, y01); y2 = fmaf(oy, m2q.x, y2);
         }
+        float2 xys = make_float2(x2, y2);
+        auto shfl2 = [](float2 v, int o) {
+            return make_float2(__shfl_xor_sync(FULLMASK, v.x, o), __shfl_xor_sync(FULLMASK, v.y, o));
+        };
 #pragma unroll
         for (int o = BWD_SLOTS; o < 32; o <<= 1) {
-            m0 += __shfl_xor_sync(FULLMASK, m0, o); m1 += __shfl_xor_sync(FULLMASK, m1, o); m2 += __shfl_xor_sync(FULLMASK, m2, o);
-            x0 += __shfl_xor_sync(FULLMASK, x0, o); x1 += __shfl_xor_sync(FULLMASK, x1, o); x2 += __shfl_xor_sync(FULLMASK, x2, o);
-            y0 += __shfl_xor_sync(FULLMASK, y0, o); y1 += __shfl_xor_sync(FULLMASK, y1, o); y2 += __shfl_xor_sync(FULLMASK, y2, o);
-            qs += __shfl_xor_sync(FULLMASK, qs, o);
-            c0 += __shfl_xor_sync(FULLMASK, c0, o); c1 += __shfl_xor_sync(FULLMASK, c1, o); c2 += __shfl_xor_sync(FULLMASK, c2, o);
-            n0 += __shfl_xor_sync(FULLMASK, n0, o); n1 += __shfl_xor_sync(FULLMASK, n1, o); n2 += __shfl_xor_sync(FULLMASK, n2, o);
+            m01 = fadd2(m01, shfl2(m01, o)); m2q = fadd2(m2q, shfl2(m2q, o));
+            x01 = fadd2(x01, shfl2(x01, o)); y01 = fadd2(y01, shfl2(y01, o));
+            xys = fadd2(xys, shfl2(xys, o));
+            c01 = fadd2(c01, shfl2(c01, o)); c2n0 = fadd2(c2n0, shfl2(c2n0, o)); n12 = fadd2(n12, shfl2(n12, o));
             so += __shfl_xor_sync(FULLMASK, so, o);
         }
+        const float m0 = m01.x, m1 = m01.y, m2 = m2q.x, qs = m2q.y, x0 = x01.x, x1 = x01.y, y0 = y01.x, y1 = y01.y;
+        const float c0 = c01.x, c1 = c01.y, c2 = c2n0.x, n0 = c2n0.y, n1 = n12.x, n2 = n12.y;
+        x2 = xys.x; y2 = xys.y;
         if (ph == 0 && ps < np) {
             float* acc = gacc + (size_t)__float_as_uint(hdr[ps].x) * GACC_STRIDE;
             red_add_v4(acc + 0, m0, m1, m2, x0);
@@ -267,6 +280,9 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
         mbar_wait(&full_bar[stage], parity);
         if (base < wlast) {
             const float4(*sb)[BWD_BATCH] = sbuf[stage];
+            uint32_t sb_addr;     // opaque to the compiler: otherwise it is rematerialised (S2UR + 5 uniform ops) per pair
+            asm volatile("mov.u32 %0, %1;" : "=r"(sb_addr) : "r"(smem_u32(&sb[0][0])));
+            constexpr uint32_t PLANE_B = BWD_BATCH * 16u;
             for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
                 if (base + c0 >= wlast) continue;
                 const int e = c0 + lane;
@@ -281,12 +297,15 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                     m &= ~(1u << bit);
                     const int j = c0 + bit;
                     const int pos = base + j;  // 0-based list position == reference `contributor`
-                    const float4 qa = sb[0][j], qb = sb[1][j], qc = sb[2][j], qd = sb[3][j];
+                    // record reads through an explicit 32-bit shared address (one uniform shift-add per pair; the generic
+                    // form made ptxas rebuild the stage's shared-window base for every pair)
+                    const uint32_t ra = sb_addr + (uint32_t)j * 16u;
+                    const float4 qa = lds128(ra), qb = lds128(ra + PLANE_B), qc = lds128(ra + 2 * PLANE_B), qd = lds128(ra + 3 * PLANE_B);
                     const PairEval ev = eval_pair(qa, qb, qc, qd, fx, fy);
                     const bool valid = ev.valid && pos < last;
                     if (!__any_sync(FULLMASK, valid)) continue;
 
-                    const float4 pn = sb[4][j], pc = sb[5][j];
+                    const float4 pn = lds128(ra + 4 * PLANE_B), pc = lds128(ra + 5 * PLANE_B);
                     float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0;
                     float gm0 = 0.f, gm1 = 0.f, gz = 0.f;
                     bool lowpass = false;
@@ -299,17 +318,17 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                         const float icd = fast_rcp(c_d);
                         const float m_d = fmaf(-MSCALE * NEAR_N, icd, MSCALE);
                         const float dmd_dd = DMD * icd * icd;
-                        const float dL_dweight = fmaf(m_d, fmaf(m_d, final_A, m2fD), final_D2) * dL_dreg;
+                        const float dL_dweight = fmaf(m_d, fmaf(m_d, rA, rB), rC);
                         // S = <this splat's channel values, the pixel's upstream gradients>; rec = the same blended over the
                         // splats behind it (one chain instead of the reference's accum_rec per channel)
-                        float S = fmaf(pn.w, dpx0, dL_dweight);
-                        S = fmaf(pc.x, dpx1, S); S = fmaf(pc.y, dpx2, S);
-                        S = fmaf(c_d, dL_ddepth, S);
-                        S = fmaf(pn.x, dn0, S); S = fmaf(pn.y, dn1, S); S = fmaf(pn.z, dn2, S);
+                        float2 sp = fmul2(make_float2(pn.x, pn.y), k_dn01);
+                        sp = ffma2(make_float2(pn.z, pn.w), k_dn2px0, sp);
+                        sp = ffma2(make_float2(pc.x, pc.y), k_px12, sp);
+                        const float S = (sp.x + sp.y) + fmaf(c_d, dL_ddepth, dL_dweight);
                         const float D = S - rec;
                         rec = fmaf(alpha, D, rec);
                         const float dL_dalpha = fmaf(D, T, k_tail * ria);
-                        float dL_dz = fmaf(fmaf(m_d, final_A, -final_D) * reg2, dmd_dd, dL_ddepth) * w;
+                        float dL_dz = fmaf(fmaf(m_d + m_d, rA, rB), dmd_dd, dL_ddepth) * w;
                         if (pos == medpos) dL_dz += dL_dmedian_depth;
                         const float v = G * dL_dalpha;                 // dL/dopacity share
                         const float dL_dG = qc.w * dL_dalpha;
@@ -317,10 +336,10 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                         if (ev.ray) {
                             // dL/ds = dL_dG * (-G) * s ;  s = p.xy / p.z ; depth = det(T) / p.z
                             const float gs = dL_dG * -G * ev.ip;
-                            const float a0 = gs * ev.s0, a1 = gs * ev.s1;
+                            o0 = fmul2s(make_float2(ev.s0, ev.s1), gs);
+                            const float a0 = o0.x, a1 = o0.y;
                             const float q = dL_dz * ev.ip;
                             const float a2 = -fmaf(a0, ev.s0, fmaf(a1, ev.s1, q * c_d));
-                            o0 = make_float2(a0, a1);
                             o1 = make_float2(a2, q);
                         } else {
                             gm0 = dL_dG * (-G * FILTER_INV_SQUARE * ev.d0);

@@ -71,8 +71,10 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
         for (int b = 0; b < 2 && b < nb; b++) issue_batch(sbuf[b], src, pstride, b * RBATCH, min(RBATCH, n - b * RBATCH), &full_bar[b]);
 
     float T = 1.0f;
-    float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f;
-    float Dacc = 0.f, M1 = 0.f, M2 = 0.f, dist = 0.f;
+    // accumulators paired for the packed FMAs (the record's (x, y) / (z, w) halves are the multiplicands):
+    // NA = (normal.x, normal.y), NC = (normal.z, colour.r), CC = (colour.g, colour.b), DM = (depth, M1)
+    float2 NA = make_float2(0.f, 0.f), NC = NA, CC = NA, DM = NA;
+    float M2 = 0.f, dist = 0.f;
     uint32_t last_contrib = 0, med_contrib = 0;   // median depth / index / normal are re-derived from med_contrib after the walk
     bool done = !inside;
     bool warp_done = __all_sync(FULLMASK, done);
@@ -106,14 +108,14 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                             const float w = ev.alpha * T;
                             const float A = 1.0f - T;
                             const float mm = MSCALE * (1.0f - NEAR_N * fast_rcp(ev.depth));
-                            dist += (mm * mm * A + M2 - 2.0f * mm * M1) * w;
-                            Dacc += ev.depth * w;
-                            M1 += mm * w;
+                            dist += (mm * mm * A + M2 - 2.0f * mm * DM.y) * w;
+                            DM = ffma2s(make_float2(ev.depth, mm), w, DM);
                             M2 += mm * mm * w;
                             const uint32_t pos = (uint32_t)(b * RBATCH + j + 1);
                             if (T > 0.5f) med_contrib = pos;          // S/forward.cu:402-408: the last splat blended while T > 0.5
-                            N0 += pn.x * w; N1 += pn.y * w; N2 += pn.z * w;
-                            C0 += pn.w * w; C1 += pc.x * w; C2 += pc.y * w;
+                            NA = ffma2s(make_float2(pn.x, pn.y), w, NA);
+                            NC = ffma2s(make_float2(pn.z, pn.w), w, NC);
+                            CC = ffma2s(make_float2(pc.x, pc.y), w, CC);
                             T = test_T;
                             last_contrib = pos;
                         }
@@ -157,6 +159,7 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
             mn0 = pn.x; mn1 = pn.y; mn2 = pn.z;
         }
         final_T[pid] = T;
+        const float C0 = NC.y, C1 = CC.x, C2 = CC.y, N0 = NA.x, N1 = NA.y, N2 = NC.x, Dacc = DM.x, M1 = DM.y;
         final_T[pid + N] = M1;
         final_T[pid + 2 * N] = M2;
         n_contrib[pid] = last_contrib;
