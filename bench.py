@@ -453,6 +453,17 @@ def train_iters(impl):
     if ours:
         v2, _ = measure_iters_per_s("ours", 100_000, 800, 800, iters=40, warmup=5, fused_ssim=False, fused_post=False)
         out["rasterizer_only"] = {"value": v2, "unit": "iters/s", "ops": "drop-in rasterizer + the reference's torch ops"}
+        try:    # the whole iteration replayed from ONE CUDA graph (the drop-in forward never blocks the stream; the reference's does)
+            from train_harness import measure_graph_iters_per_s
+            v3, _, overflow = measure_graph_iters_per_s(100_000, 800, 800, iters=200, warmup=5)
+            out["cuda_graph"] = {"value": v3, "unit": "iters/s", "capture_overflow": overflow,
+                                 "ops": "same iteration, loss kept on the device, recorded once with torch.cuda.graph and replayed "
+                                        "(render + losses + backward + statistics + capturable Adam = 1 graph launch per iteration)"}
+        except Exception as e:  # noqa: BLE001
+            out["cuda_graph"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    else:
+        out["cuda_graph"] = {"unavailable": "the reference forward blocks on a cudaMemcpy of num_rendered "
+                                            "(S/cuda_rasterizer/rasterizer_impl.cu:282): it cannot be captured"}
     for name, kw in (("config3_scaffold2dgs", dict(P=400_000, W=1600, H=1060, scaffold=True)),
                      ("config4_pgsr", dict(P=1_000_000, W=1600, H=900, pgsr=True))):
         try:

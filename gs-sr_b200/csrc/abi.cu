@@ -24,7 +24,7 @@ __global__ void mark_visible_kernel(int, const float*, const ViewParams, uint8_t
 cudaError_t launch_sh_forward(int, int, int, const float*, const float*, const float*, const int*, float*, uint8_t*, cudaStream_t);
 cudaError_t launch_sh_backward(int, int, int, const float*, const float*, const float*, const uint8_t*, const int*, const float*,
                                float*, float*, cudaStream_t);
-__global__ void tile_scan(int, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, const int*, uint32_t, volatile uint32_t*, uint32_t);
+__global__ void tile_scan(int, const uint32_t*, uint32_t*, uint32_t*, uint32_t*, const int*, uint32_t, volatile uint32_t*, uint32_t, int);
 __global__ void scatter_keys(int, const float*, const float*, int, const CullRec*, const float*, const int*,
                              const uint32_t*, int, int, uint32_t*, uint64_t*, uint32_t);
 __global__ void sort_build_records(const uint32_t*, uint64_t*, const GeomRec*, const float*, int, int, int, float4*,
@@ -174,16 +174,29 @@ static RHistEntry g_hist[32];
 static int g_hist_n = 0;
 static uint64_t g_hist_clock = 0;
 static int g_force_cap = 0;                      // option "force_capacity": tests of the overflow path
+static int g_capture_margin = 150;               // option "capture_margin": capacity of a captured forward, % of the history
 static thread_local int g_true_R = 0;
 
-static uint32_t predicted_capacity(int dev, int family, int W, int H) {
+// CUDA-graph capture.  A forward that is being RECORDED (cudaStreamIsCapturing) cannot wait for num_rendered and cannot
+// re-run: it lays the binning buffer out for capture_margin % (default 150) of the history of earlier EAGER forwards of
+// the same configuration and enqueues every kernel exactly once; the lists of a replay whose num_rendered outgrows that
+// capacity stay clamped (a truncated frame, never an out-of-bounds access) and tile_scan leaves the count in a sticky
+// host word that gsr_capture_overflow() reports, so the caller can re-capture.  The reference cannot be captured at all
+// (blocking cudaMemcpy in the middle of its forward, S/cuda_rasterizer/rasterizer_impl.cu:282).
+static bool stream_capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return st == cudaStreamCaptureStatusActive;
+}
+
+static uint32_t predicted_capacity(int dev, int family, int W, int H, bool capturing = false) {
     if (g_force_cap > 0) return (uint32_t)g_force_cap;
     std::lock_guard<std::mutex> lk(g_hist_mu);
     for (int i = 0; i < g_hist_n; i++) {
         RHistEntry& e = g_hist[i];
         if (e.dev == dev && e.family == family && e.W == W && e.H == H) {
             e.stamp = ++g_hist_clock;
-            const double c = fmin(2.0e9, 1.25 * e.hist + 4096.0);
+            const double c = fmin(2.0e9, (capturing ? 0.01 * g_capture_margin : 1.25) * e.hist + 4096.0);
             return (uint32_t)((((uint64_t)c + 4095) / 4096) * 4096);
         }
     }
@@ -220,6 +233,9 @@ static volatile uint32_t* my_host_slot() {
     return mine;
 }
 static thread_local uint32_t g_seq = 0;
+static const char* const kNoHistory =
+    "%s: the stream is being captured into a CUDA graph but this (device, rasterizer, resolution) has no num_rendered "
+    "history -- run at least one eager forward of the same configuration before capturing";
 
 // Wait until tile_scan has published sequence number `seq`; rb = {R, prefiltered flag}.  Pure host-memory polling;
 // the stream is queried now and then so that a faulted kernel turns into an error instead of a hang.
@@ -286,11 +302,21 @@ int gsr_set_option(const char* name, int value) {
     if (!strcmp(name, "dbg")) { g_dbg = value; return GSR_OK; }
     if (!strcmp(name, "no_used_bits")) { g_no_used_bits = value ? 1 : 0; return GSR_OK; }
     if (!strcmp(name, "force_capacity")) { g_force_cap = value > 0 ? value : 0; return GSR_OK; }
+    if (!strcmp(name, "capture_margin")) { g_capture_margin = value >= 100 ? value : 100; return GSR_OK; }
     set_error("gsr_set_option: unknown option %s", name);
     return GSR_E_INVALID;
 }
 
 int gsr_last_num_rendered(void) { return g_true_R; }
+
+unsigned int gsr_capture_overflow(int reset) {
+    volatile uint32_t* slot = my_host_slot();
+    if (!slot) return 0u;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const uint32_t v = slot[3];
+    if (reset) slot[3] = 0u;
+    return v;
+}
 
 int gsr_profile_enable(int on) {
     // applies to the CURRENT device (events are per device); the on/off switch is global
@@ -386,9 +412,11 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         BinWs::carve(bw, align256(bbase), (int64_t)cap, P);
         return GSR_OK;
     };
+    const bool capturing = stream_capturing(s);
     auto scan = [&](uint32_t cap, volatile uint32_t* slot, uint32_t seq) -> int {
         prof_begin(GSR_PROF_SCAN, s);
-        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total, gw.flags, cap, slot, seq);
+        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total, gw.flags, cap, slot, seq,
+                                     capturing ? 1 : 0);
         prof_end(GSR_PROF_SCAN, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         return GSR_OK;
@@ -428,8 +456,15 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
         volatile uint32_t* slot = my_host_slot();
         if (!slot) { set_error("cudaHostAlloc of the num_rendered slot failed"); return GSR_E_CUDA; }
         const uint32_t seq = ++g_seq;
-        const uint32_t cap = predicted_capacity(dev, 0, W, H);
+        const uint32_t cap = predicted_capacity(dev, 0, W, H, capturing);
         int rc;
+        if (capturing) {
+            if (cap == 0) { set_error(kNoHistory, "gsr_surfel_forward"); return GSR_E_INVALID; }
+            if ((rc = lay_out(cap)) < 0) return rc;
+            if ((rc = scan(cap, slot, seq)) < 0) return rc;
+            if ((rc = bin_and_render(cap)) < 0) return rc;
+            return (int)cap;      // recorded once; nothing to wait for (see "CUDA-graph capture")
+        }
         if (cap > 0) {
             if ((rc = lay_out(cap)) < 0) return rc;
             if ((rc = scan(cap, slot, seq)) < 0) return rc;
@@ -463,7 +498,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     (void)N;
     ht.mark("launch_rest");
     ht.flush("forward");
-    if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (debug && !capturing) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return R;
 }
 
@@ -514,7 +549,7 @@ int gsr_surfel_backward(int P, int D, int M, int R, const float* background, int
     if (shs && M > 0) GSR_CUDA_CHECK(launch_sh_backward(P, D, M, means3D, campos, shs, gw.clamped, radii, dL_dcolor, dL_dsh, dL_dmean3D, s));
     prof_end(GSR_PROF_PREPROCESS_BWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
-    if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (debug && !stream_capturing(s)) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return GSR_OK;
 }
 
@@ -616,9 +651,11 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
         BinWs::carve(bw, align256(bbase), (int64_t)cap, P, nplanes, EWA_GACC);
         return GSR_OK;
     };
+    const bool capturing = stream_capturing(s);
     auto scan = [&](uint32_t cap, volatile uint32_t* slot, uint32_t seq) -> int {
         prof_begin(GSR_PROF_SCAN, s);
-        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total, gw.flags, cap, slot, seq);
+        tile_scan<<<1, 1024, 0, s>>>(ntiles, iw.tile_count, iw.tile_offset, iw.tile_cursor, iw.total, gw.flags, cap, slot, seq,
+                                     capturing ? 1 : 0);
         prof_end(GSR_PROF_SCAN, s);
         GSR_CUDA_CHECK(cudaGetLastError());
         return GSR_OK;
@@ -659,8 +696,15 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
         if (!slot) { set_error("cudaHostAlloc of the num_rendered slot failed"); return GSR_E_CUDA; }
         const uint32_t seq = ++g_seq;
         const int family = a.geo ? 3 : (a.plane ? 2 : 1);
-        const uint32_t cap = predicted_capacity(dev, family, W, H);
+        const uint32_t cap = predicted_capacity(dev, family, W, H, capturing);
         int rc;
+        if (capturing) {
+            if (cap == 0) { set_error(kNoHistory, who); return GSR_E_INVALID; }
+            if ((rc = lay_out(cap)) < 0) return rc;
+            if ((rc = scan(cap, slot, seq)) < 0) return rc;
+            if ((rc = bin_and_render(cap, false)) < 0) return rc;
+            return (int)cap;
+        }
         if (cap > 0) {
             if ((rc = lay_out(cap)) < 0) return rc;
             if ((rc = scan(cap, slot, seq)) < 0) return rc;
@@ -688,7 +732,7 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
         if ((rc = bin_and_render(0, false)) < 0) return rc;
     }
     R = (int)layout;
-    if (a.debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (a.debug && !capturing) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return R;
 }
 
@@ -753,7 +797,7 @@ static int ewa_backward(const EwaBwdArgs& a, const char* who) {
     if (a.shs && a.M > 0) GSR_CUDA_CHECK(launch_sh_backward(P, a.D, a.M, a.means3D, a.campos, a.shs, gw.clamped, a.radii, a.dL_dcolor, a.dL_dsh, a.dL_dmean3D, s));
     prof_end(GSR_PROF_PREPROCESS_BWD, s);
     GSR_CUDA_CHECK(cudaGetLastError());
-    if (a.debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (a.debug && !stream_capturing(s)) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return GSR_OK;
 }
 }  // namespace gsr
@@ -846,7 +890,7 @@ int gsr_visible_filter(int P, int width, int height, const float* means3D, const
         P, 0, 0, means3D, scales, (const float4*)rotations, nullptr, nullptr, cov3D_precomp, true, vc, focal_x, focal_y,
         tan_fovx, tan_fovy, false, true, radii, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     GSR_CUDA_CHECK(cudaGetLastError());
-    if (debug) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (debug && !stream_capturing(s)) GSR_CUDA_CHECK(cudaStreamSynchronize(s));
     return GSR_OK;
 }
 

@@ -26,7 +26,7 @@ namespace gsr {
 __global__ void __launch_bounds__(1024)
 tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
           uint32_t* __restrict__ cursors, uint32_t* __restrict__ total, const int* __restrict__ flags, uint32_t cap,
-          volatile uint32_t* host_slot, uint32_t seq) {
+          volatile uint32_t* host_slot, uint32_t seq, int sticky) {
     // cap = number of list entries the binning buffer was laid out for.  The host sizes that buffer BEFORE it knows R
     // (from earlier frames), so the lists the later kernels see are clamped to it: offsets[] saturate at cap and
     // scatter_keys drops entries at positions >= cap.  R itself goes to the host, which re-runs binning and rendering
@@ -68,6 +68,9 @@ tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict_
         offsets[ntiles] = min(carry, cap); total[0] = carry; total[1] = (uint32_t)flags[0];
         if (host_slot != nullptr) {
             host_slot[1] = carry; host_slot[2] = (uint32_t)flags[0];
+            // sticky (forwards recorded into a CUDA graph: nobody waits on the slot, the lists stay clamped): leave the
+            // count in slot[3] when it exceeds the capacity the graph was captured with, for gsr_capture_overflow()
+            if (sticky && (carry > cap || flags[0])) host_slot[3] = carry > cap ? carry : 0xffffffffu;
             __threadfence_system();
             host_slot[0] = seq;
         }

@@ -92,6 +92,9 @@ def lib():
         L.gsr_surfel_audit.argtypes = [C.c_int] * 4 + [_fp] * 5 + [C.c_void_p]
         L.gsr_ewa_audit.restype = C.c_int
         L.gsr_ewa_audit.argtypes = [C.c_int] * 5 + [_fp] * 5 + [C.c_void_p]
+    if hasattr(L, "gsr_capture_overflow"):
+        L.gsr_capture_overflow.restype = C.c_uint
+        L.gsr_capture_overflow.argtypes = [C.c_int]
     _LIB = L
     return L
 

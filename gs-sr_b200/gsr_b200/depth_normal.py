@@ -51,7 +51,8 @@ class _DepthNormal(torch.autograd.Function):
 
 def _kinv(intrinsic_matrix, device):
     # ndc_2_cam (:86): cam_xyz @ torch.inverse(intrinsic.t()) -- the same float32 op on the same device, no host read-back
-    return torch.inverse(intrinsic_matrix.to(device=device, dtype=torch.float32).t()).contiguous()
+    # linalg.inv_ex = torch.inverse's factorisation without its status read-back (no stream sync, graph-capturable)
+    return torch.linalg.inv_ex(intrinsic_matrix.to(device=device, dtype=torch.float32).t())[0].contiguous()
 
 
 def render_normal_weighted(depth, intrinsic_matrix, weight=None):

@@ -10,7 +10,8 @@
 
 Values and gradients w.r.t. ``allmap`` equal autograd's through the reference ops (tests/test_surfel_post_gpu.py), except
 that pixels with zero alpha get a zero gradient where the reference's 0/0 division adjoint produces NaN.  The tiny per-view
-camera algebra (two 3x3 inverses, as in depths_to_points) stays in torch on the device: no host synchronisation.
+camera algebra (two small inverses, as in depths_to_points) stays in torch on the device (``linalg.inv_ex``: no host
+synchronisation, capturable into a CUDA graph).
 No CPU / PyTorch fallback for the image-sized work.
 """
 from __future__ import annotations
@@ -21,15 +22,34 @@ from . import check, lib
 from ._torch_util import f32c, on_device, stream_ptr
 
 
+def _inv(m):
+    """torch.inverse without its error check: the same LU factorisation (identical values), but no device->host read
+    of the status word -- torch.inverse synchronises the stream, which also makes it illegal during CUDA-graph capture."""
+    return torch.linalg.inv_ex(m)[0]
+
+
+_NDC2PIX = {}
+
+
+def _ndc2pix(W, H, device):
+    """The constant matrix of depths_to_points (:14-17), uploaded once per (W, H, device): building it from a Python
+    list on every call is a synchronous host->device copy (and cannot be recorded into a CUDA graph)."""
+    key = (W, H, str(device))
+    m = _NDC2PIX.get(key)
+    if m is None:
+        m = torch.tensor([[W / 2, 0, 0, W / 2], [0, H / 2, 0, H / 2], [0, 0, 0, 1]], dtype=torch.float32, device=device).T
+        _NDC2PIX[key] = m
+    return m
+
+
 def _camera_constants(world_view_transform, full_proj_transform, W, H):
     """K, rays_o, R packed as 21 floats on the device -- the same float32 torch ops as depths_to_points (:10-22)."""
     wvt = world_view_transform.float()
-    c2w = (wvt.T).inverse()
-    ndc2pix = torch.tensor([[W / 2, 0, 0, W / 2], [0, H / 2, 0, H / 2], [0, 0, 0, 1]], dtype=torch.float32,
-                           device=wvt.device).T
+    c2w = _inv(wvt.T)
+    ndc2pix = _ndc2pix(W, H, wvt.device)
     projection_matrix = c2w.T @ full_proj_transform.float()
     intrins = (projection_matrix @ ndc2pix)[:3, :3].T
-    K = intrins.inverse().T @ c2w[:3, :3].T
+    K = _inv(intrins).T @ c2w[:3, :3].T
     return torch.cat([K.reshape(9), c2w[:3, 3].reshape(3), wvt[:3, :3].reshape(9)]).contiguous()
 
 

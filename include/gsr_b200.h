@@ -98,6 +98,20 @@ int gsr_set_option(const char* name, int value);
  * num_rendered of this host thread's most recent forward: */
 int gsr_last_num_rendered(void);
 
+/* CUDA-graph capture (no reference counterpart: the reference forward contains a blocking cudaMemcpy and cannot be
+ * captured).  When the stream handed to a *_forward entry point is being captured (cudaStreamIsCapturing), the call
+ * records every kernel of the forward exactly once and returns without waiting for num_rendered: the binning buffer
+ * is laid out for "capture_margin" percent (gsr_set_option, default 150, minimum 100) of the num_rendered history of
+ * earlier EAGER forwards of the same (device, rasterizer, resolution) -- at least one is required, otherwise the call
+ * fails with GSR_E_INVALID.  The buffer callbacks run at capture time (with torch: inside the graph's private pool).
+ * A replay whose num_rendered outgrows the captured capacity renders a TRUNCATED frame (lists clamped to the
+ * capacity; memory safe) and leaves that count in a sticky host word of the capturing thread:
+ *   gsr_capture_overflow(reset) returns it (0 = every replay fitted; 0xffffffff = a `prefiltered` violation) and
+ *   clears it when reset != 0.  Read it after the replay has completed (any stream / event sync of the caller),
+ *   from the host thread that captured the graph; on overflow raise the margin or run an eager forward (which
+ *   refreshes the history) and capture again.  Backward entry points have no host interaction and capture as they are. */
+unsigned int gsr_capture_overflow(int reset);
+
 /* Decision audit of a finished forward (verification only, no reference counterpart).  Re-walks the record stream
  * kept in the forward's binning / image buffers with the render kernels' own arithmetic and writes, per pixel, the
  * smallest relative distance of any blend decision to its threshold:

@@ -50,7 +50,7 @@ class _RefSurfelFn(torch.autograd.Function):
 
 class MiniTwoDGSTrainer:
     def __init__(self, P=100_000, W=800, H=800, seed=0, impl="ours", lambda_dssim=0.2, lambda_normal=0.05,
-                 lambda_dist=100.0, depth_ratio=0.0, device="cuda"):
+                 lambda_dist=100.0, depth_ratio=0.0, device="cuda", capturable=False):
         self.impl, self.W, self.H, self.device = impl, W, H, device
         self.lambda_dssim, self.lambda_normal, self.lambda_dist, self.depth_ratio = lambda_dssim, lambda_normal, lambda_dist, depth_ratio
         sc = synth.make_scene(P, W, H, seed=seed, sh=True)
@@ -72,7 +72,7 @@ class MiniTwoDGSTrainer:
             {"params": [self.features_rest], "lr": 2.5e-3 / 20.0, "name": "f_rest"},
             {"params": [self.opacity], "lr": 0.05, "name": "opacity"},
             {"params": [self.scaling], "lr": 5e-3, "name": "scaling"},
-            {"params": [self.rotation], "lr": 1e-3, "name": "rotation"}], lr=0.0, eps=1e-15)
+            {"params": [self.rotation], "lr": 1e-3, "name": "rotation"}], lr=0.0, eps=1e-15, capturable=capturable)
         self.xyz_gradient_accum = torch.zeros((P, 1), device=device)
         self.denom = torch.zeros((P, 1), device=device)
         self.max_radii2D = torch.zeros((P,), device=device)
@@ -186,6 +186,44 @@ class MiniTwoDGSTrainer:
         self.optimizer.step()
         self.optimizer.zero_grad(set_to_none=True)
         return loss_value, {k: float(v.detach()) for k, v in losses.items()}
+
+
+    # ---- the same iteration without host round trips, for CUDA-graph capture ------------------------------
+    def step_device(self):
+        """step() with its three host interactions removed -- the per-step `loss.item()` and the two boolean-mask
+        gathers/scatters of the densification statistics (data-dependent shapes) written as `torch.where` / masked adds
+        (identical values) -- so that the whole iteration (render, losses, backward, statistics, Adam) can be recorded
+        into ONE CUDA graph.  Only the drop-in rasterizer allows that: the reference forward blocks on a cudaMemcpy.
+        Returns the loss as a device tensor; gradients are left in place (zero_grad happens before the capture)."""
+        out = self.render()
+        losses = self.loss_dict(out)
+        loss = sum(losses.values())
+        loss.backward()
+        with torch.no_grad():
+            vis = out["visibility_filter"]
+            self.max_radii2D.copy_(torch.where(vis, torch.max(self.max_radii2D, out["radii"].float()), self.max_radii2D))
+            g = out["viewspace_points"].grad
+            visf = vis.unsqueeze(1).float()
+            self.xyz_gradient_accum += torch.norm(g[:, :2], dim=-1, keepdim=True) * visf
+            self.denom += visf
+        self.optimizer.step()
+        return loss.detach()
+
+    def capture(self, warmup=3):
+        """Eager warm-up on a side stream (num_rendered history, allocator, optimizer state), then one captured
+        iteration.  Returns (graph, static loss tensor); every graph.replay() is one training iteration."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.optimizer.zero_grad(set_to_none=True)
+                self.step_device()
+        torch.cuda.current_stream().wait_stream(side)
+        self.optimizer.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.step_device()
+        return graph, loss
 
 
 class MiniScaffold2DGSTrainer(MiniTwoDGSTrainer):
@@ -663,6 +701,26 @@ def anchor_growing_candidates(tr, grad_threshold=0.0002, update_depth=3, update_
         new_feat = scatter_max_rows(new_feat, inverse, uniq.shape[0])[keep]
         out.append((candidate_anchor, new_feat))
     return out
+
+
+def measure_graph_iters_per_s(P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, fused_ssim=True, fused_post=True):
+    """2DGS iterations replayed from ONE CUDA graph (drop-in rasterizer + fused image-space ops; the reference arm has no
+    counterpart, its forward cannot be captured).  Returns (iters/s, last loss, capture_overflow())."""
+    from gsr_b200.graphs import capture_overflow
+    tr = MiniTwoDGSTrainer(P, W, H, seed=seed, impl="ours", capturable=True)
+    tr.fused_ssim, tr.fused_post = fused_ssim, fused_post
+    graph, loss = tr.capture(warmup=max(warmup, 3))
+    capture_overflow(reset=True)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return iters / (e0.elapsed_time(e1) * 1e-3), float(loss), capture_overflow(reset=True)
 
 
 def measure_iters_per_s(impl, P=100_000, W=800, H=800, iters=30, warmup=5, seed=0, scaffold=False, pgsr=False,
