@@ -174,4 +174,62 @@ __device__ __forceinline__ bool tile_may_contribute(const CullRec& r, float cx, 
     return false;
 }
 
+// ---- warp-cooperative tile counting ---------------------------------------------------------
+// The forward preprocess kernels (one thread per Gaussian) count, per tile of the Gaussian's getRect rectangle, the
+// tiles the splat can reach.  Rectangles are 4.7 tiles on average but 14.5 for the largest of a warp's 32 Gaussians
+// (cfg-B), so a per-thread loop over the rectangle ran with 2-10 of 32 lanes active and made up 82 % of the kernel's
+// instructions (ncu, profiles/r02b_*).  Here the warp flattens its 32 rectangles into one list of (Gaussian, tile)
+// items (prefix sum of the areas) and every lane tests item base + lane: the owner is found by a 5-step binary search
+// over the prefix (shuffles), its CullRec comes out of shared memory, and the decision is the SAME
+// tile_may_contribute() call with the same operands, so counts, masks and the scatter's re-test agree bit for bit.
+// ALL 32 lanes must call it (area = 0: nothing to test).  Returns the lane's own hit mask over the first 32 tiles
+// of its rectangle (row-major).  s_rec: [4][32] float4 of this warp, s_mask: [32] words of this warp.
+__device__ __forceinline__ uint32_t warp_count_tiles(const CullRec& cr, float cx, float cy, int x0, int y0, int w, int area,
+                                                     int gx, uint32_t* __restrict__ tile_count, float4 (*s_rec)[32],
+                                                     uint32_t* s_mask) {
+    const int lane = threadIdx.x & 31;
+    int incl = area;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - area;
+    s_rec[0][lane] = cr.q0;
+    s_rec[1][lane] = cr.q1;
+    s_rec[2][lane] = make_float4(cr.q2.x, cr.q2.y, cr.q2.z, cx);
+    s_rec[3][lane] = make_float4(cy, __int_as_float(x0), __int_as_float(y0), __int_as_float(w));
+    s_mask[lane] = 0u;
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+        const int t = base + lane;
+        // owner = the last lane whose exclusive prefix is <= t (lanes with area 0 share their successor's prefix and are
+        // never the last one below an item that exists)
+        int o = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int e = __shfl_sync(0xffffffffu, excl, (o + step) & 31);
+            if (e <= t) o += step;
+        }
+        const int k = t - __shfl_sync(0xffffffffu, excl, o);
+        if (t < total) {
+            CullRec r;
+            r.q0 = s_rec[0][o];
+            r.q1 = s_rec[1][o];
+            const float4 a = s_rec[2][o], b = s_rec[3][o];
+            r.q2 = make_float4(a.x, a.y, a.z, 0.f);
+            const int ow = __float_as_int(b.w);
+            const int ry = k / ow, rx = k - ry * ow;
+            const int tx = __float_as_int(b.y) + rx, ty = __float_as_int(b.z) + ry;
+            if (tile_may_contribute(r, a.w, b.x, tx, ty)) {
+                atomicAdd(&tile_count[(size_t)(ty * gx + tx) * TILE_CTR_STRIDE], 1u);
+                if (k < 32) atomicOr(&s_mask[o], 1u << k);
+            }
+        }
+    }
+    __syncwarp();
+    return s_mask[lane];
+}
+
 }  // namespace gsr

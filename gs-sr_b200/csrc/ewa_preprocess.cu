@@ -92,12 +92,16 @@ ewa_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D, const
                    uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_count, float* __restrict__ rgb,
                    uint8_t* __restrict__ clamped, int* __restrict__ flags) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    __shared__ float4 s_rec[kRadiiOnly ? 1 : 8][4][32];      // warp_count_tiles (cull.cuh); unused by the radii-only filter
+    __shared__ uint32_t s_mask[kRadiiOnly ? 1 : 8][32];
     int radius_out = 0;
-    uint32_t mask_out = 0;
     float view[16];
     load16(vc.view, view);
-    do {
+    CullRec cr_t;
+    cr_t.q0 = cr_t.q1 = cr_t.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cx_t = 0.f, cy_t = 0.f;
+    int x0_t = 0, y0_t = 0, w_t = 1, area_t = 0;
+    if (idx < P) do {
         const float3 p = make_float3(__ldg(means3D + 3 * (size_t)idx), __ldg(means3D + 3 * (size_t)idx + 1),
                                      __ldg(means3D + 3 * (size_t)idx + 2));
         const float3 pv = xform43_pinned(view, p);
@@ -168,20 +172,22 @@ ewa_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D, const
         g.b = make_float4(conic.z, opa, tau, (float)mode);
         geom[idx] = g;
         depths[idx] = pv.z;
-        // tiles of the reference rect (G/auxiliary.h:46-56) the splat can actually reach
-        const int w = x1 - x0, area = w * (y1 - y0);
-        uint32_t m = 0;
-        int k = 0;
-        for (int ty = y0; ty < y1; ty++)
-            for (int tx = x0; tx < x1; tx++, k++)
-                if (tile_may_contribute(cr, px, py, tx, ty)) {
-                    atomicAdd(&tile_count[(size_t)(ty * vc.gx + tx) * TILE_CTR_STRIDE], 1u);
-                    if (k < 32) m |= 1u << k;
-                }
-        mask_out = area <= 32 ? m : MASK_RETEST;
+        cr_t = cr; cx_t = px; cy_t = py;
+        x0_t = x0; y0_t = y0; w_t = x1 - x0; area_t = w_t * (y1 - y0);
     } while (0);
-    radii[idx] = radius_out;
-    if (!kRadiiOnly) masks[idx] = mask_out;
+    if (kRadiiOnly) {
+        if (idx < P) radii[idx] = radius_out;
+        return;
+    }
+    // tiles of the reference rect (G/auxiliary.h:46-56) the splat can actually reach, counted by the whole warp over
+    // the flattened (Gaussian, tile) list (cull.cuh)
+    const int wic = threadIdx.x >> 5;
+    const uint32_t m = warp_count_tiles(cr_t, cx_t, cy_t, x0_t, y0_t, w_t, area_t, vc.gx, tile_count,
+                                        s_rec[kRadiiOnly ? 0 : wic], s_mask[kRadiiOnly ? 0 : wic]);
+    if (idx < P) {
+        radii[idx] = radius_out;
+        masks[idx] = area_t == 0 ? 0u : (area_t <= 32 ? m : MASK_RETEST);
+    }
 }
 
 template __global__ void ewa_preprocess_fwd<false>(int, int, int, const float*, const float*, const float4*, const float*,

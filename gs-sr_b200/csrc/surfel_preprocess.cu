@@ -61,13 +61,18 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
                       int* __restrict__ radii, GeomRec* __restrict__ geom, CullRec* __restrict__ cull, float* __restrict__ depths,
                       uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_count, float* __restrict__ rgb,
                       uint8_t* __restrict__ clamped, int* __restrict__ flags) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
+    __shared__ float4 s_rec[8][4][32];        // warp_count_tiles: the CullRec + rectangle of each lane, per warp
+    __shared__ uint32_t s_mask[8][32];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int radius_out = 0;
-    uint32_t mask_out = 0;
     float view[16];
     load16(vc.view, view);
-    do {
+    // what the warp-cooperative tile count needs of this thread's Gaussian (area 0: culled or out of range)
+    CullRec cr_t;
+    cr_t.q0 = cr_t.q1 = cr_t.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cx_t = 0.f, cy_t = 0.f;
+    int x0_t = 0, y0_t = 0, w_t = 1, area_t = 0;
+    if (idx < P) do {
         float3 p = make_float3(__ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1), __ldg(means3D + 3 * idx + 2));
         float3 pv = xform43_pinned(view, p);
         if (pv.z <= 0.2f) {  // in_frustum, S/auxiliary.h:187-212
@@ -141,21 +146,17 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
         geom[idx] = g;
         depths[idx] = pv.z;
         radius_out = ri;
-        // tiles of the reference rect (S/auxiliary.h:69-79) that the splat can actually reach:
-        // count them per tile (bucket sizes) and remember which ones as a bit mask
-        const int w = x1 - x0, area = w * (y1 - y0);
-        uint32_t m = 0;
-        int k = 0;
-        for (int ty = y0; ty < y1; ty++)
-            for (int tx = x0; tx < x1; tx++, k++)
-                if (tile_may_contribute(cr, cx, cy, tx, ty)) {
-                    atomicAdd(&tile_count[(size_t)(ty * vc.gx + tx) * TILE_CTR_STRIDE], 1u);
-                    if (k < 32) m |= 1u << k;
-                }
-        mask_out = area <= 32 ? m : MASK_RETEST;
+        cr_t = cr; cx_t = cx; cy_t = cy;
+        x0_t = x0; y0_t = y0; w_t = x1 - x0; area_t = w_t * (y1 - y0);
     } while (0);
-    radii[idx] = radius_out;
-    masks[idx] = mask_out;
+    // tiles of the reference rect (S/auxiliary.h:69-79) that the splat can actually reach: counted per tile (bucket
+    // sizes) and remembered as a bit mask -- by the whole warp over the flattened (Gaussian, tile) list (cull.cuh)
+    const int wic = threadIdx.x >> 5;
+    const uint32_t m = warp_count_tiles(cr_t, cx_t, cy_t, x0_t, y0_t, w_t, area_t, vc.gx, tile_count, s_rec[wic], s_mask[wic]);
+    if (idx < P) {
+        radii[idx] = radius_out;
+        masks[idx] = area_t == 0 ? 0u : (area_t <= 32 ? m : MASK_RETEST);
+    }
 }
 
 // quat_to_rotmat_vjp, S/auxiliary.h:240-284. vR columns c0,c1,c2 (column-major).
