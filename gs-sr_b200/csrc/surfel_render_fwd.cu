@@ -35,7 +35,10 @@ constexpr int FWD_SPLIT = 8 / FWD_WARPS;
 
 // MARK: P < 2^23, the record word has room for the per-warp-block "blended" marks handed to the backward
 template <bool MARK>
-__global__ void __launch_bounds__(FWD_WARPS * 32, 32 / FWD_WARPS)
+#ifndef GSR_FWD_MINB
+#define GSR_FWD_MINB (32 / FWD_WARPS)
+#endif
+__global__ void __launch_bounds__(FWD_WARPS * 32, GSR_FWD_MINB)
 surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W,
                   int H, int gx, const float* __restrict__ bg, float* __restrict__ final_T,
                   uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
