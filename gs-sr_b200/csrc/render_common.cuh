@@ -7,7 +7,11 @@
 
 namespace gsr {
 
-constexpr int RBATCH = 128;                       // record entries per shared-memory stage
+#ifndef GSR_RBATCH
+#define GSR_RBATCH 224                            // measured at cfg-B: 64 -> 1132 us, 128 -> 1097, 192 -> 1086, 224 -> 1080 (43 KB of static smem)
+#endif
+constexpr int RBATCH = GSR_RBATCH;                // record entries per shared-memory stage of the forward kernels (multiple of 32)
+static_assert(RBATCH % 32 == 0 && 2 * 6 * RBATCH * 16 <= 47 * 1024, "forward stage size");
 constexpr uint32_t FULLMASK = 0xffffffffu;
 constexpr float MSCALE = FAR_N / (FAR_N - NEAR_N);              // S/forward.cu:396
 constexpr float DMD = (FAR_N * NEAR_N) / (FAR_N - NEAR_N);      // S/backward.cu:348
