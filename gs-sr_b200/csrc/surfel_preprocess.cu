@@ -172,7 +172,10 @@ __device__ __forceinline__ float4 quat_vjp(float4 q, float3 v0, float3 v1, float
 }
 
 // One thread per Gaussian; every output row is written (zeros when radii == 0).
-__global__ void __launch_bounds__(256)
+#ifndef GSR_PREBWD_MINB
+#define GSR_PREBWD_MINB 3      // 85 registers, 3 CTAs/SM: 132 -> 125 us at cfg-B (4 spills: 144 us)
+#endif
+__global__ void __launch_bounds__(256, GSR_PREBWD_MINB)
 surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
                       const float2* __restrict__ scales, const float4* __restrict__ rotations,
                       const float* __restrict__ shs, const bool precomp, const ViewParams vc,
