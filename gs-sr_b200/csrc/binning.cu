@@ -104,45 +104,72 @@ tile_scan(int ntiles, const uint32_t* __restrict__ counts, uint32_t* __restrict_
 }
 
 // ---- 3. scatter (depth, index) keys into tile buckets ---------------------------------------
+// One thread per Gaussian loads its rectangle and the mask of reachable tiles the preprocess recorded; the (Gaussian, tile)
+// pairs of the warp's 32 Gaussians are then flattened into one list (prefix sum of the mask popcounts) and every lane
+// takes item base + lane: owner by a 5-step search over the prefix, the item's tile = the k-th set bit of the owner's mask,
+// one returning atomicAdd on the tile's cursor, one 8-byte key store.  Four rounds (128 items) issue their atomics before
+// the first result is needed.  The kernel is bound by memory round trips, not by issue: a per-thread loop over the mask
+// (the round-1 version) needed as many dependent rounds as the busiest of the warp's 32 Gaussians had tiles / 4.
 __global__ void __launch_bounds__(256)
 scatter_keys(int P, const float* __restrict__ centre_x, const float* __restrict__ centre_y, int centre_stride,
              const CullRec* __restrict__ cull,
              const float* __restrict__ depths, const int* __restrict__ radii, const uint32_t* __restrict__ masks, int gx, int gy,
              uint32_t* __restrict__ cursors, uint64_t* __restrict__ keys, uint32_t cap) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    // all five per-Gaussian loads are issued together (one memory round trip; values of culled Gaussians are in
-    // bounds and ignored), then the gates
-    const int r = __ldg(radii + idx);
-    const uint32_t mask = __ldg(masks + idx);
-    const float cx = __ldg(centre_x + (size_t)idx * centre_stride), cy = __ldg(centre_y + (size_t)idx * centre_stride);
-    const uint32_t dbits = __float_as_uint(__ldg(depths + idx));
-    if (r <= 0 || mask == 0u) return;
-    const uint64_t key = ((uint64_t)dbits << 32) | (uint32_t)idx;
-    int x0, y0, x1, y1;
-    get_rect(cx, cy, r, gx, gy, x0, y0, x1, y1);
-    if (mask != MASK_RETEST) {
-        // the preprocess recorded which tiles of the (<= 32 tile) rect passed the test; up to four returning
-        // atomics are in flight per round (the kernel is bound by memory round trips, not by issue)
-        const int w = x1 - x0;
-        uint32_t m = mask;
-        while (m) {
-            uint32_t pos[4];
-            int cnt = 0;
+    const int lane = threadIdx.x & 31;
+    const bool in_range = idx < P;
+    const int li = in_range ? idx : P - 1;           // out-of-range lanes of the last warp load a valid row and ignore it
+    // all five per-Gaussian loads are issued together (one memory round trip), then the gates
+    const int r = __ldg(radii + li);
+    const uint32_t mask = __ldg(masks + li);
+    const float cx = __ldg(centre_x + (size_t)li * centre_stride), cy = __ldg(centre_y + (size_t)li * centre_stride);
+    const uint32_t dbits = __float_as_uint(__ldg(depths + li));
+    const bool live = in_range && r > 0 && mask != 0u;
+    const bool retest = live && mask == MASK_RETEST;   // rectangle of more than 32 tiles: no mask, the tile test is repeated
+    int x0 = 0, y0 = 0, x1 = 1, y1 = 1;
+    if (live) get_rect(cx, cy, r, gx, gy, x0, y0, x1, y1);
+    const int w = max(x1 - x0, 1);
+    const uint32_t m = (live && !retest) ? mask : 0u;
+    const int cnt = __popc(m);
+    int incl = cnt;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (m) {
-                    const int k = __ffs(m) - 1;
-                    m &= m - 1;
-                    pos[u] = atomicAdd(&cursors[(size_t)((y0 + k / w) * gx + (x0 + k % w)) * TILE_CTR_STRIDE], 1u);
-                    cnt = u + 1;
-                }
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - cnt;
+    for (int base = 0; base < total; base += 128) {
+        uint32_t pos[4], klo[4], khi[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int t = base + u * 32 + lane;
+            int o = 0;            // owner = the last lane whose exclusive prefix is <= t
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int e = __shfl_sync(0xffffffffu, excl, o + step);
+                if (e <= t) o += step;
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (u < cnt && pos[u] < cap) keys[pos[u]] = key;
+            const int k = t - __shfl_sync(0xffffffffu, excl, o);
+            const uint32_t mo = __shfl_sync(0xffffffffu, m, o);
+            const int xo = __shfl_sync(0xffffffffu, x0, o), yo = __shfl_sync(0xffffffffu, y0, o), wo = __shfl_sync(0xffffffffu, w, o);
+            klo[u] = __shfl_sync(0xffffffffu, (uint32_t)idx, o);
+            khi[u] = __shfl_sync(0xffffffffu, dbits, o);
+            ok[u] = t < total;
+            pos[u] = 0u;
+            if (ok[u]) {
+                const int bit = (int)__fns(mo, 0u, k + 1);             // k-th (0-based) reachable tile of the owner's rectangle
+                const int ry = bit / wo, rx = bit - ry * wo;
+                pos[u] = atomicAdd(&cursors[(size_t)((yo + ry) * gx + (xo + rx)) * TILE_CTR_STRIDE], 1u);
+            }
         }
-    } else {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (ok[u] && pos[u] < cap) keys[pos[u]] = ((uint64_t)khi[u] << 32) | klo[u];
+    }
+    if (retest) {
+        const uint64_t key = ((uint64_t)dbits << 32) | (uint32_t)idx;
         const CullRec cr = cull[idx];
         for (int y = y0; y < y1; y++)
             for (int x = x0; x < x1; x++)
