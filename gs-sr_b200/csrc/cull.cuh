@@ -127,17 +127,18 @@ __device__ __forceinline__ float det_eval_rn(float xx, float xy, float yy, float
     return __fadd_rn(__fmaf_rn(t0, x, __fmul_rn(t1, y)), c0);
 }
 
+// Branch-free on purpose: the sub-tests (disc, centre inside, four corners, four edges) are all evaluated and OR-ed.  The
+// warp-cooperative callers run 32 different (Gaussian, tile) items per instruction; with early returns the items of a
+// round left the function at ten different points and the remaining code re-ran per lane subset (1-4 active threads,
+// 350 instructions per round instead of ~130 -- ncu, profiles/r02_prof_binning_summary.txt).
 __device__ __forceinline__ bool tile_may_contribute(const CullRec& r, float cx, float cy, int tx, int ty) {
     const int mode = (int)r.q2.z;
-    if (mode == CULL_ALWAYS) return true;
-    if (mode == CULL_NEVER) return false;
     const float gx0 = __fadd_rn((float)(tx * TILE), -CULL_MARGIN), gx1 = __fadd_rn((float)(tx * TILE + TILE - 1), CULL_MARGIN);
     const float gy0 = __fadd_rn((float)(ty * TILE), -CULL_MARGIN), gy1 = __fadd_rn((float)(ty * TILE + TILE - 1), CULL_MARGIN);
-    {   // low-pass disc
-        const float dx = fmaxf(fmaxf(__fadd_rn(gx0, -cx), __fadd_rn(cx, -gx1)), 0.f);
-        const float dy = fmaxf(fmaxf(__fadd_rn(gy0, -cy), __fadd_rn(cy, -gy1)), 0.f);
-        if (__fmaf_rn(dx, dx, __fmul_rn(dy, dy)) <= r.q1.z) return true;
-    }
+    // low-pass disc
+    const float ddx = fmaxf(fmaxf(__fadd_rn(gx0, -cx), __fadd_rn(cx, -gx1)), 0.f);
+    const float ddy = fmaxf(fmaxf(__fadd_rn(gy0, -cy), __fadd_rn(cy, -gy1)), 0.f);
+    int hit = __fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy)) <= r.q1.z;
     const float xx = r.q0.x, xy = r.q0.y, yy = r.q0.z, bx = r.q0.w, by = r.q1.x, c0 = r.q1.y;
     const float x0 = __fadd_rn(gx0, -r.q2.x), x1 = __fadd_rn(gx1, -r.q2.x);
     const float y0 = __fadd_rn(gy0, -r.q2.y), y1 = __fadd_rn(gy1, -r.q2.y);
@@ -152,26 +153,29 @@ __device__ __forceinline__ bool tile_may_contribute(const CullRec& r, float cx, 
     const float dm = __fmul_rn(QUADRIC_EPS, __fmaf_rn(xx, yy, __fmul_rn(xy, xy)));
     const float tolx = __fmaf_rn(X, dm, __fmul_rn(QUADRIC_EPS, __fmaf_rn(axy, aby, __fmul_rn(yy, abx))));
     const float toly = __fmaf_rn(Y, dm, __fmul_rn(QUADRIC_EPS, __fmaf_rn(axy, abx, __fmul_rn(xx, aby))));
-    if (ex >= __fadd_rn(__fmul_rn(x0, det), -tolx) && ex <= __fadd_rn(__fmul_rn(x1, det), tolx) &&
-        ey >= __fadd_rn(__fmul_rn(y0, det), -toly) && ey <= __fadd_rn(__fmul_rn(y1, det), toly)) return true;
-    if (det_eval_rn(xx, xy, yy, bx, by, c0, x0, y0) <= E || det_eval_rn(xx, xy, yy, bx, by, c0, x1, y0) <= E ||
-        det_eval_rn(xx, xy, yy, bx, by, c0, x0, y1) <= E || det_eval_rn(xx, xy, yy, bx, by, c0, x1, y1) <= E) return true;
+    // centre of the ellipse inside the rectangle
+    hit |= (ex >= __fadd_rn(__fmul_rn(x0, det), -tolx)) & (ex <= __fadd_rn(__fmul_rn(x1, det), tolx)) &
+           (ey >= __fadd_rn(__fmul_rn(y0, det), -toly)) & (ey <= __fadd_rn(__fmul_rn(y1, det), toly));
+    // a corner inside the ellipse
+    hit |= (det_eval_rn(xx, xy, yy, bx, by, c0, x0, y0) <= E) | (det_eval_rn(xx, xy, yy, bx, by, c0, x1, y0) <= E) |
+           (det_eval_rn(xx, xy, yy, bx, by, c0, x0, y1) <= E) | (det_eval_rn(xx, xy, yy, bx, by, c0, x1, y1) <= E);
+    // an edge crossing the ellipse: interior minimum of the 1-D restriction
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const float yc = k ? y1 : y0;
         const float B = __fmaf_rn(xy, yc, bx);
         const float C = __fadd_rn(__fmul_rn(__fmaf_rn(yy, yc, __fmul_rn(2.f, by)), yc), c0);
         const float BB = __fmul_rn(B, B);
-        if (-B > __fmul_rn(x0, xx) && -B < __fmul_rn(x1, xx) &&
-            __fmul_rn(C, xx) <= __fadd_rn(BB, __fmaf_rn(E, xx, __fmul_rn(QUADRIC_EPS, BB)))) return true;
+        hit |= (-B > __fmul_rn(x0, xx)) & (-B < __fmul_rn(x1, xx)) &
+               (__fmul_rn(C, xx) <= __fadd_rn(BB, __fmaf_rn(E, xx, __fmul_rn(QUADRIC_EPS, BB))));
         const float xc = k ? x1 : x0;
         const float B2 = __fmaf_rn(xy, xc, by);
         const float C2 = __fadd_rn(__fmul_rn(__fmaf_rn(xx, xc, __fmul_rn(2.f, bx)), xc), c0);
         const float BB2 = __fmul_rn(B2, B2);
-        if (-B2 > __fmul_rn(y0, yy) && -B2 < __fmul_rn(y1, yy) &&
-            __fmul_rn(C2, yy) <= __fadd_rn(BB2, __fmaf_rn(E, yy, __fmul_rn(QUADRIC_EPS, BB2)))) return true;
+        hit |= (-B2 > __fmul_rn(y0, yy)) & (-B2 < __fmul_rn(y1, yy)) &
+               (__fmul_rn(C2, yy) <= __fadd_rn(BB2, __fmaf_rn(E, yy, __fmul_rn(QUADRIC_EPS, BB2))));
     }
-    return false;
+    return mode == CULL_ALWAYS ? true : (mode == CULL_NEVER ? false : hit != 0);
 }
 
 // ---- warp-cooperative tile counting ---------------------------------------------------------
