@@ -40,7 +40,8 @@ ewa_build_records(const uint32_t* __restrict__ offsets, uint64_t* __restrict__ k
     __shared__ BucketSortSmem bs;
     const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs);
     const float ox = (float)((tile % gx) * TILE), oy = (float)((tile / gx) * TILE);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll 2
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {      // two entries' gathers in flight per thread (as in sort_build_records)
         const uint32_t g = (uint32_t)(sorted[i] & 0xffffffffull);
         const float4* gp = reinterpret_cast<const float4*>(geom + g);
         const float4 ga = __ldg(gp), gb = __ldg(gp + 1);

@@ -141,7 +141,8 @@ __device__ __forceinline__ const uint64_t* sort_tile_bucket(uint64_t* __restrict
     if (n > 32 && n <= BUCKET_SORT_CAP && !force_bitonic) {
         uint64_t* a = skeys;
         uint64_t* b = skeys + BUCKET_SORT_CAP;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = gk[i];
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = gk[i];      // all of a thread's key loads in flight together
         __syncthreads();
         if (bucket_sort_256(a, b, n, bs)) return a;
         // degenerate depth distribution: fall through to the bitonic network on the keys still in a[]
