@@ -51,6 +51,9 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+#ifndef GSR_BWD_PAIR2
+#define GSR_BWD_PAIR2 0         // evaluating two walked entries before their gradients: 1.76 -> 1.93 ms (the kernel is bound by the
+#endif                          // shared-memory pipe and sits at its register cap; the forward gains 2 % from the same change)
 #ifndef GSR_BWD_BATCH
 #define GSR_BWD_BATCH 32
 #endif
@@ -292,18 +295,11 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                     else hit = entry_hits_block(sb[0][e], sb[1][e], sb[2][e], sb[3][e], bx0, bx1, by0, by1);
                 }
                 uint32_t m = __ballot_sync(FULLMASK, hit);
-                while (m) {
-                    const int bit = 31 - __clz(m);
-                    m &= ~(1u << bit);
-                    const int j = c0 + bit;
-                    const int pos = base + j;  // 0-based list position == reference `contributor`
-                    // record reads through an explicit 32-bit shared address (one uniform shift-add per pair; the generic
-                    // form made ptxas rebuild the stage's shared-window base for every pair)
-                    const uint32_t ra = sb_addr + (uint32_t)j * 16u;
-                    const float4 qa = lds128(ra), qb = lds128(ra + PLANE_B), qc = lds128(ra + 2 * PLANE_B), qd = lds128(ra + 3 * PLANE_B);
-                    const PairEval ev = eval_pair(qa, qb, qc, qd, fx, fy);
+                // gradient of one evaluated pair (list position pos, record at shared address ra); the state chain T / rec runs
+                // through it back to front
+                auto pair_grad = [&](const PairEval& ev, const float opac, const float qdw, const uint32_t ra, const int pos) {
                     const bool valid = ev.valid && pos < last;
-                    if (!__any_sync(FULLMASK, valid)) continue;
+                    if (!__any_sync(FULLMASK, valid)) return;
 
                     const float4 pn = lds128(ra + 4 * PLANE_B), pc = lds128(ra + 5 * PLANE_B);
                     float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0;
@@ -331,7 +327,7 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                         float dL_dz = fmaf(fmaf(m_d + m_d, rA, rB), dmd_dd, dL_ddepth) * w;
                         if (pos == medpos) dL_dz += dL_dmedian_depth;
                         const float v = G * dL_dalpha;                 // dL/dopacity share
-                        const float dL_dG = qc.w * dL_dalpha;
+                        const float dL_dG = opac * dL_dalpha;
                         o2 = make_float2(w, v);
                         if (ev.ray) {
                             // dL/ds = dL_dG * (-G) * s ;  s = p.xy / p.z ; depth = det(T) / p.z
@@ -348,7 +344,7 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                             lowpass = true;
                         }
                     }
-                    const uint32_t g = __float_as_uint(qd.w) & (USED ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS);
+                    const uint32_t g = __float_as_uint(qdw) & (USED ? REC_INDEX_MASK_USED : ~REC_FLAG_ALWAYS);
                     float* slot = pend + npend * SLOT_STRIDE + lane * PAIR_VALS;
                     *reinterpret_cast<float2*>(slot) = o0;
                     *reinterpret_cast<float2*>(slot + 2) = o1;
@@ -360,7 +356,36 @@ surfel_render_bwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                         if (lane == 0) { atomicAdd(acc + 17, r2); atomicAdd(acc + 18, r0); atomicAdd(acc + 19, r1); }
                     }
                     if (++npend == BWD_SLOTS) { flush(BWD_SLOTS); npend = 0; }
+                };
+#if GSR_BWD_PAIR2
+                // two walked entries at a time: their evaluations are independent chains and hide each other's latencies
+                while (m) {
+                    const int b1 = 31 - __clz(m);
+                    m &= ~(1u << b1);
+                    const bool two = m != 0u;
+                    const int b2 = two ? 31 - __clz(m) : b1;
+                    if (two) m &= ~(1u << b2);
+                    const uint32_t r1 = sb_addr + (uint32_t)(c0 + b1) * 16u, r2 = sb_addr + (uint32_t)(c0 + b2) * 16u;
+                    const float4 c1 = lds128(r1 + 2 * PLANE_B), d1 = lds128(r1 + 3 * PLANE_B);
+                    const float4 c2 = lds128(r2 + 2 * PLANE_B), d2 = lds128(r2 + 3 * PLANE_B);
+                    const PairEval e1 = eval_pair(lds128(r1), lds128(r1 + PLANE_B), c1, d1, fx, fy);
+                    const PairEval e2 = eval_pair(lds128(r2), lds128(r2 + PLANE_B), c2, d2, fx, fy);
+                    pair_grad(e1, c1.w, d1.w, r1, base + c0 + b1);
+                    if (two) pair_grad(e2, c2.w, d2.w, r2, base + c0 + b2);
                 }
+#else
+                while (m) {
+                    const int bit = 31 - __clz(m);
+                    m &= ~(1u << bit);
+                    const int j = c0 + bit;
+                    // record reads through an explicit 32-bit shared address (one uniform shift-add per pair; the generic
+                    // form made ptxas rebuild the stage's shared-window base for every pair)
+                    const uint32_t ra = sb_addr + (uint32_t)j * 16u;
+                    const float4 qa = lds128(ra), qb = lds128(ra + PLANE_B), qc = lds128(ra + 2 * PLANE_B), qd = lds128(ra + 3 * PLANE_B);
+                    const PairEval ev = eval_pair(qa, qb, qc, qd, fx, fy);
+                    pair_grad(ev, qc.w, qd.w, ra, base + j);      // base + j: 0-based list position == reference `contributor`
+                }
+#endif
             }
         }
         // release the stage; the last of the CTA's warps to arrive refills it with the batch BWD_STAGES ahead.

@@ -35,6 +35,9 @@ constexpr int FWD_SPLIT = 8 / FWD_WARPS;
 
 // MARK: P < 2^23, the record word has room for the per-warp-block "blended" marks handed to the backward
 template <bool MARK>
+#ifndef GSR_FWD_PAIR2
+#define GSR_FWD_PAIR2 1        // 1.079 -> 1.059 ms at cfg-B
+#endif
 #ifndef GSR_FWD_MINB
 #define GSR_FWD_MINB (32 / FWD_WARPS)
 #endif
@@ -95,12 +98,9 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                 if (e < cnt) hit = entry_hits_block(sb[0][e], sb[1][e], sb[2][e], sb[3][e], bx0, bx1, by0, by1);
                 uint32_t m = __ballot_sync(FULLMASK, hit);
                 uint32_t used = 0;                 // entries of this chunk blended on >= 1 pixel of this warp's block
-                while (m) {
-                    const int bitpos = __ffs(m) - 1;
+                // blend of one evaluated survivor (entry j = c0 + bitpos); the state chain T / done runs through it in list order
+                auto blend = [&](const PairEval& ev, int bitpos) {
                     const int j = c0 + bitpos;
-                    m &= m - 1;
-                    const float4 qa = sb[0][j], qb = sb[1][j], qc = sb[2][j], qd = sb[3][j];
-                    PairEval ev = eval_pair(qa, qb, qc, qd, fx, fy);
                     bool valid = ev.valid && !done;
                     if (__any_sync(FULLMASK, valid)) {
                         const float test_T = T * (1.0f - ev.alpha);
@@ -123,7 +123,31 @@ surfel_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __rest
                             last_contrib = pos;
                         }
                     }
+                };
+#if GSR_FWD_PAIR2
+                // survivors two at a time: the two evaluations are independent instruction chains (each ends in a MUFU.EX2
+                // behind a MUFU.RCP), interleaved they hide each other's latencies; the blends follow in list order
+                while (m) {
+                    const int b1 = __ffs(m) - 1;
+                    m &= m - 1;
+                    const bool two = m != 0u;
+                    const int b2 = two ? __ffs(m) - 1 : b1;
+                    m &= m - 1;          // (0 & anything stays 0)
+                    const int j1 = c0 + b1, j2 = c0 + b2;
+                    const PairEval e1 = eval_pair(sb[0][j1], sb[1][j1], sb[2][j1], sb[3][j1], fx, fy);
+                    const PairEval e2 = eval_pair(sb[0][j2], sb[1][j2], sb[2][j2], sb[3][j2], fx, fy);
+                    blend(e1, b1);
+                    if (two) blend(e2, b2);
                 }
+#else
+                while (m) {
+                    const int bitpos = __ffs(m) - 1;
+                    const int j = c0 + bitpos;
+                    m &= m - 1;
+                    const PairEval ev = eval_pair(sb[0][j], sb[1][j], sb[2][j], sb[3][j], fx, fy);
+                    blend(ev, bitpos);
+                }
+#endif
                 // checked once per 32-entry chunk: after the last pixel finishes, the rest of the chunk only evaluates
                 if (__all_sync(FULLMASK, done)) warp_done = true;
                 // hand the contributing entries to the backward: one predicated red.or per chunk into the record word
