@@ -223,6 +223,21 @@ def test_heavy_tiles_take_the_large_sort_paths(P):
     assert np.array_equal(alt["color"], out["color"]) and np.array_equal(alt["others"], out["others"])
 
 
+def test_image_with_more_than_8192_tiles():
+    """2560x1440 = 160 x 90 = 14 400 tiles: tile_scan's chunks exceed its register-resident size (8 tiles per thread) and
+    take the generic path; large and small splats, compared with the reference build (or the oracle without it)."""
+    from oracle import refcuda
+    W, H, P = 2560, 1440, 60_000
+    sc = synth.make_scene(P, W, H, seed=77, sigma_px=7.0)
+    gc, go = synth.make_upstream_grads(W, H, seed=78)
+    tt = hz.to_torch(sc)
+    out = hz.run_product_surfel(sc, gc, go, tt=tt)
+    ref = hz.run_refcuda_surfel(sc, gc, go, tt=tt) if refcuda.available("surfel") else hz.run_oracle_surfel(sc, gc, go)
+    assert (out["radii"] > 0).sum() > 0.8 * P
+    assert_forward_close(out, ref)
+    assert_grads_close(out["grads"], ref["grads"], grad_keys({}, sc))
+
+
 def test_product_matches_reference_cuda_build():
     from oracle import refcuda
     if not refcuda.available("surfel"):
