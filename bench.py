@@ -18,7 +18,7 @@ One JSON line on rank 0:
   step_ms: median / p10 / p90 of the K per-step event times (BASELINE.md's reporting protocol)
   evals  : K_eval (per tile 256 x list entries walked before the block exits, reference definition,
            counted by the CPU port on the full frame) and FP32 pair evaluations/s = K_eval / step time
-  extras : the other hot-path workloads (cfg-A surfel, 3DGS 1M, plane cfg-4, visible_filter 2M, distCUDA2 1M), same
+  extras : the other hot-path workloads (cfg-A surfel, 3DGS 1M, plane cfg-4, visible_filter 2M, distCUDA2 1M, SSIM loss, TSDF fusion), same
            timing for both arms (tests/bench_extras.py)
   train  : BASELINE's "train iters/s" on config 2, with the fused image-space ops and rasterizer-only
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".

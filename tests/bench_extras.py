@@ -6,6 +6,8 @@ that every row of DESIGN.md's speed table comes out of a driver-run bench line:
   cfg4_plane       PGSR plane rasterizer fwd+bwd, P=1M, 1600x900, render_geo             (BASELINE config 4 stand-in)
   visible_filter   scaffold_filter.visible_filter on 2M anchors @ 1600x1060               (BASELINE config 3 prefilter)
   dist2_knn3       simple_knn distCUDA2 on 1M points
+  ssim_loss        SSIM loss fwd+bwd, 3x1060x1600 (reference arm: the reference's conv2d formulation in torch, same GPU)
+  tsdf_fuse        TSDF fusion, 256^3 samples x 32 views @ 1600x1060 (reference arm: the reference's per-view torch rule)
 
 Each entry: {"ms": device time per call (CUDA events, inputs resident, median of the timed calls), "value": units/s,
 "unit": ...}.  Test/bench infrastructure: imports the drop-in packages for our arm and oracle/refcuda.py (ctypes front-end
@@ -173,12 +175,57 @@ def dist2_knn3(impl, P=1_000_000):
     return _entry(ev_times(fn, 5, 2), P, "points/s")
 
 
+def ssim_loss(impl, H=1060, W=1600):
+    """SSIM loss forward + backward on a 3 x 1060 x 1600 image: the fused kernels against the reference's five 121-tap
+    depthwise conv2d + autograd formulation (oracle/ssim_oracle.py restates vanilla_scene.py:32-61 with torch ops) on the
+    same GPU."""
+    import torch
+    x = torch.rand((3, H, W), device="cuda", generator=torch.Generator("cuda").manual_seed(1)).requires_grad_(True)
+    y = torch.rand((3, H, W), device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    if impl == "ours":
+        from gsr_b200.ssim import ssim
+    else:
+        from oracle.ssim_oracle import ssim
+
+    def fn():
+        x.grad = None
+        ssim(x, y).backward()
+    return _entry(ev_times(fn, 20, 3), 3 * H * W, "pixel-channels/s")
+
+
+def tsdf_fuse(impl, Ng=256):
+    """TSDF fusion of a 256^3 sample chunk against 32 depth maps @ 1600x1060 (extract_mesh_unbounded's inner call):
+    gsr_tsdf_fuse against the reference's per-view torch rule (tests/tsdf_synth.py restates mesh_utils.py:195-246 with the
+    same torch ops) on the same GPU."""
+    import torch
+    from tsdf_synth import build_tsdf_case, torch_rule_unbounded
+    c = build_tsdf_case("bench")
+    ax = torch.linspace(-1.2, 1.2, Ng, device="cuda")
+    xx, yy, zz = torch.meshgrid(ax, ax, ax, indexing="ij")
+    pts = torch.stack([xx.ravel(), yy.ravel(), zz.ravel()], -1).contiguous()
+    projs = [torch.from_numpy(m).cuda() for m in c["projs"]]
+    depths = [torch.from_numpy(d).cuda() for d in c["depthmaps"]]
+    if impl == "ours":
+        from gsr_b200.tsdf import TSDFFusion
+        f = TSDFFusion(projs, depths, None, center=c["center"], radius=c["radius"])
+        fn = lambda: f.compute_unbounded_tsdf(pts, True, c["voxel_size"])  # noqa: E731
+        n, w = 5, 2
+    else:
+        center = torch.from_numpy(c["center"]).cuda()
+        fn = lambda: torch_rule_unbounded(pts, projs, depths, None, center, c["radius"], c["voxel_size"])  # noqa: E731
+        n, w = 2, 1
+    return _entry(ev_times(fn, n, w), pts.shape[0] * len(projs), "sample-views/s")
+
+
 WORKLOADS = {
     "cfgA_surfel": (lambda impl: surfel_cfg_a(impl), "surfel"),
     "gauss_1m": (lambda impl: ewa(impl, False), "gaussian"),
     "cfg4_plane": (lambda impl: ewa(impl, True), "plane"),
     "visible_filter": (lambda impl: visible_filter(impl), "filter"),
     "dist2_knn3": (lambda impl: dist2_knn3(impl), "knn"),
+    # the reference arm of the next two is the reference's own torch formulation (no oracle/_ref library involved)
+    "ssim_loss": (lambda impl: ssim_loss(impl), None),
+    "tsdf_fuse": (lambda impl: tsdf_fuse(impl), None),
 }
 
 
@@ -189,7 +236,7 @@ def run_all(impl):
     for name, (fn, variant) in WORKLOADS.items():
         if impl != "ours":
             from oracle import refcuda
-            if not refcuda.available(variant):
+            if variant is not None and not refcuda.available(variant):
                 out[name] = {"unavailable": f"oracle/_ref/libref_{variant}.so absent"}
                 continue
         try:

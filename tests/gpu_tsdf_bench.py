@@ -19,31 +19,9 @@ center = torch.from_numpy(c["center"]).cuda(); radius = c["radius"]; vs = c["vox
 f = TSDFFusion(projs, depths, rgbs, center=c["center"], radius=radius)
 
 
-def torch_rule(samples, return_rgb=False):
-    """mesh_utils.py:195-246 with the same torch ops (GPU tensors), the reference arm of this helper."""
-    norm = torch.linalg.norm(samples, dim=-1)
-    mask = norm > 1
-    sdf_trunc = 5 * vs * torch.ones_like(samples[:, 0])
-    sdf_trunc[mask] *= 1 / (2 - norm[mask].clamp(max=1.9))
-    mag = norm[..., None]
-    samples = torch.where(mag < 1, samples, (1 / (2 - mag) * (samples / mag))) * radius + center
-    tsdfs = torch.ones_like(samples[:, 0]); rgbo = torch.zeros((samples.shape[0], 3), device="cuda")
-    weights = torch.ones_like(samples[:, 0])
-    for i in range(len(projs)):
-        new_points = torch.cat([samples, torch.ones_like(samples[..., :1])], dim=-1) @ projs[i]
-        z = new_points[..., -1:]
-        pix = new_points[..., :2] / new_points[..., -1:]
-        mask_proj = ((pix > -1.) & (pix < 1.) & (z > 0)).all(dim=-1)
-        sd = torch.nn.functional.grid_sample(depths[i][None], pix[None, None], mode='bilinear', padding_mode='border', align_corners=True).reshape(-1, 1)
-        sr = torch.nn.functional.grid_sample(rgbs[i][None], pix[None, None], mode='bilinear', padding_mode='border', align_corners=True).reshape(3, -1).T
-        sdf = (sd - z).flatten()
-        mask_proj = mask_proj & (sdf > -sdf_trunc)
-        sdf = torch.clamp(sdf / sdf_trunc, min=-1.0, max=1.0)[mask_proj]
-        w = weights[mask_proj]; wp = w + 1
-        tsdfs[mask_proj] = (tsdfs[mask_proj] * w + sdf) / wp
-        rgbo[mask_proj] = (rgbo[mask_proj] * w[:, None] + sr[mask_proj]) / wp[:, None]
-        weights[mask_proj] = wp
-    return tsdfs
+def torch_rule(samples):
+    from tsdf_synth import torch_rule_unbounded
+    return torch_rule_unbounded(samples, projs, depths, rgbs, center, radius, vs)
 
 
 def timed(fn, n):

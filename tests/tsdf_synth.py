@@ -114,3 +114,38 @@ def build_tsdf_case(name, n=None):
     return dict(samples=samples, contracted=contracted, center=center, radius=radius, voxel_size=voxel,
                 projs=[c["full_proj"] for c in cams], depthmaps=[m[0] for m in maps], rgbmaps=[m[1] for m in maps],
                 eyes=np.array(eyes, dtype=np.float64))
+
+
+def torch_rule_unbounded(samples, projs, depths, rgbs, center, radius, voxel_size):
+    """The per-view torch rule of GaussianExtractor.extract_mesh_unbounded (mesh_utils.py:195-246) with the same torch ops
+    on whatever device the tensors live on -- the reference arm of the TSDF timing (tests/bench_extras.py,
+    tests/gpu_tsdf_bench.py).  rgbs may be None (depth only)."""
+    import torch
+    norm = torch.linalg.norm(samples, dim=-1)
+    mask = norm > 1
+    sdf_trunc = 5 * voxel_size * torch.ones_like(samples[:, 0])
+    sdf_trunc[mask] *= 1 / (2 - norm[mask].clamp(max=1.9))
+    mag = norm[..., None]
+    samples = torch.where(mag < 1, samples, (1 / (2 - mag) * (samples / mag))) * radius + center
+    tsdfs = torch.ones_like(samples[:, 0])
+    rgbo = torch.zeros((samples.shape[0], 3), device=samples.device)
+    weights = torch.ones_like(samples[:, 0])
+    for i in range(len(projs)):
+        new_points = torch.cat([samples, torch.ones_like(samples[..., :1])], dim=-1) @ projs[i]
+        z = new_points[..., -1:]
+        pix = new_points[..., :2] / new_points[..., -1:]
+        mask_proj = ((pix > -1.) & (pix < 1.) & (z > 0)).all(dim=-1)
+        sd = torch.nn.functional.grid_sample(depths[i][None], pix[None, None], mode='bilinear', padding_mode='border',
+                                             align_corners=True).reshape(-1, 1)
+        sdf = (sd - z).flatten()
+        mask_proj = mask_proj & (sdf > -sdf_trunc)
+        sdf = torch.clamp(sdf / sdf_trunc, min=-1.0, max=1.0)[mask_proj]
+        w = weights[mask_proj]
+        wp = w + 1
+        tsdfs[mask_proj] = (tsdfs[mask_proj] * w + sdf) / wp
+        if rgbs is not None:
+            sr = torch.nn.functional.grid_sample(rgbs[i][None], pix[None, None], mode='bilinear', padding_mode='border',
+                                                 align_corners=True).reshape(3, -1).T
+            rgbo[mask_proj] = (rgbo[mask_proj] * w[:, None] + sr[mask_proj]) / wp[:, None]
+        weights[mask_proj] = wp
+    return tsdfs
