@@ -217,20 +217,23 @@ static void record_num_rendered(int dev, int family, int W, int H, uint32_t R) {
     g_hist[slot].stamp = ++g_hist_clock;
 }
 
-// pinned, mapped, portable host words: slot = {sequence number, R, prefiltered flag, -}; one slot per host thread
+// pinned, mapped, portable host words: slot = {sequence number, R, prefiltered flag, sticky overflow}; TWO slots per host
+// thread -- the one eager forwards wait on, and one that only forwards recorded into CUDA graphs write (a graph replaying
+// on another stream must not overwrite the sequence number an eager forward of the same thread is waiting for)
 static uint32_t* g_slots = nullptr;
 static std::atomic<int> g_slot_next{0};
 static std::mutex g_slot_mu;
-static volatile uint32_t* my_host_slot() {
+static volatile uint32_t* my_host_slot(bool capture = false) {
     thread_local volatile uint32_t* mine = nullptr;
-    if (mine) return mine;
-    std::lock_guard<std::mutex> lk(g_slot_mu);
-    if (!g_slots) {
-        if (cudaHostAlloc((void**)&g_slots, 256 * 16, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return nullptr;
-        memset(g_slots, 0, 256 * 16);
+    if (!mine) {
+        std::lock_guard<std::mutex> lk(g_slot_mu);
+        if (!g_slots) {
+            if (cudaHostAlloc((void**)&g_slots, 256 * 32, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) return nullptr;
+            memset(g_slots, 0, 256 * 32);
+        }
+        mine = g_slots + 8 * (g_slot_next.fetch_add(1) % 256);
     }
-    mine = g_slots + 4 * (g_slot_next.fetch_add(1) % 256);
-    return mine;
+    return mine + (capture ? 4 : 0);
 }
 static thread_local uint32_t g_seq = 0;
 static const char* const kNoHistory =
@@ -310,7 +313,7 @@ int gsr_set_option(const char* name, int value) {
 int gsr_last_num_rendered(void) { return g_true_R; }
 
 unsigned int gsr_capture_overflow(int reset) {
-    volatile uint32_t* slot = my_host_slot();
+    volatile uint32_t* slot = my_host_slot(true);
     if (!slot) return 0u;
     std::atomic_thread_fence(std::memory_order_acquire);
     const uint32_t v = slot[3];
@@ -453,7 +456,7 @@ int gsr_surfel_forward(gsr_buffer_fn geometryBuffer, gsr_buffer_fn binningBuffer
     if (P > 0) {
         int dev = 0;
         GSR_CUDA_CHECK(cudaGetDevice(&dev));
-        volatile uint32_t* slot = my_host_slot();
+        volatile uint32_t* slot = my_host_slot(capturing);
         if (!slot) { set_error("cudaHostAlloc of the num_rendered slot failed"); return GSR_E_CUDA; }
         const uint32_t seq = ++g_seq;
         const uint32_t cap = predicted_capacity(dev, 0, W, H, capturing);
@@ -692,7 +695,7 @@ static int ewa_forward(const EwaFwdArgs& a, const char* who) {
     if (P > 0) {
         int dev = 0;
         GSR_CUDA_CHECK(cudaGetDevice(&dev));
-        volatile uint32_t* slot = my_host_slot();
+        volatile uint32_t* slot = my_host_slot(capturing);
         if (!slot) { set_error("cudaHostAlloc of the num_rendered slot failed"); return GSR_E_CUDA; }
         const uint32_t seq = ++g_seq;
         const int family = a.geo ? 3 : (a.plane ? 2 : 1);

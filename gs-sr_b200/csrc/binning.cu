@@ -192,7 +192,9 @@ sort_build_records(const uint32_t* __restrict__ offsets, uint64_t* __restrict__ 
     const int n = (int)(end - begin);
     if (n == 0) return;
     __shared__ BucketSortSmem bs;
-    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs, (dbg & 1) != 0);   // dbg bit 0: bitonic only
+    // scratch of a large tile's sort: the tile's slice of record plane 0 (n x 16 bytes, written only after the sort)
+    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs, reinterpret_cast<uint64_t*>(planes + begin),
+                                              (dbg & 1) != 0);   // dbg bit 0: bitonic only
     const float ox = (float)((tile % gx) * TILE), oy = (float)((tile / gx) * TILE);
 #ifndef GSR_BUILD_UNROLL
 #define GSR_BUILD_UNROLL 2       // two entries' gathers in flight per thread: 275 -> 252 us at cfg-B (4: 254)

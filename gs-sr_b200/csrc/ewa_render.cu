@@ -38,7 +38,7 @@ ewa_build_records(const uint32_t* __restrict__ offsets, uint64_t* __restrict__ k
     const int n = (int)(end - begin);
     if (n == 0) return;
     __shared__ BucketSortSmem bs;
-    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs);
+    const uint64_t* sorted = sort_tile_bucket(keys + begin, n, skeys, bs, reinterpret_cast<uint64_t*>(planes + begin));
     const float ox = (float)((tile % gx) * TILE), oy = (float)((tile / gx) * TILE);
 #pragma unroll 2
     for (int i = threadIdx.x; i < n; i += blockDim.x) {      // two entries' gathers in flight per thread (as in sort_build_records)

@@ -133,11 +133,101 @@ __device__ __forceinline__ bool bucket_sort_256(uint64_t* __restrict__ src, uint
     return true;
 }
 
+// ---- bucketed sort of a LARGE tile (n > BUCKET_SORT_CAP), keys in global memory ----------------------------------
+// The same three steps as bucket_sort_256 -- linear depth buckets, a counting scatter, rank counting per key inside its
+// bucket -- with the two key arrays in global memory (gk: the tile's keys, gtmp: n words of scratch) and up to 2048
+// buckets whose counters live in the 32 KB that hold the keys of a small tile.  A tile of 12 000 entries took 585 us in
+// the 105-step global-memory bitonic network it replaces (one CTA, two dependent global round trips per step); real
+// scenes have such tiles even where the blend terminates early, because the whole list must be in order first.
+// Returns true with the sorted keys back in gk, or false (gk intact) when a bucket exceeds BIG_BUCKET_MAX keys
+// (degenerate depth distribution: the rank loop is quadratic in the bucket size).
+constexpr int BIG_BUCKETS_MAX = 2048;
+constexpr int BIG_BUCKET_MAX = 256;
+__device__ __forceinline__ bool bucket_sort_global(uint64_t* __restrict__ gk, uint64_t* __restrict__ gtmp, int n,
+                                                   uint32_t* __restrict__ scnt, uint32_t* __restrict__ scur, uint32_t* sflags) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int B = 64;                                             // ~8 keys per bucket, power of two in [64, BIG_BUCKETS_MAX]
+    while (B < BIG_BUCKETS_MAX && B * 8 < n) B <<= 1;
+    if (threadIdx.x == 0) { sflags[0] = 0xffffffffu; sflags[1] = 0u; sflags[2] = 0u; }
+    for (int i = threadIdx.x; i < B; i += blockDim.x) scnt[i] = 0u;
+    __syncthreads();
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t d = (uint32_t)(gk[i] >> 32);
+        lo = min(lo, d); hi = max(hi, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { atomicMin(&sflags[0], lo); atomicMax(&sflags[1], hi); }
+    __syncthreads();
+    const uint32_t dmin = sflags[0];
+    const float scale = (float)B / ((float)(sflags[1] - dmin) + 1.0f);
+    const int Bm1 = B - 1;
+    auto bucket_of = [&](uint64_t key) -> int {            // monotonic in the depth bits, as in bucket_sort_256
+        const uint32_t off = (uint32_t)(key >> 32) - dmin;
+        return min((int)(__uint2float_rz(off) * scale), Bm1);
+    };
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&scnt[bucket_of(gk[i])], 1u);
+    __syncthreads();
+    // exclusive scan of the B counters: each warp scans a contiguous slice, then the warp totals are scanned
+    {
+        const int per_warp = B / nwarp;                     // B >= 64, nwarp = 8: a multiple of 8
+        const int per_lane = (per_warp + 31) / 32;
+        const int w0 = warp * per_warp;
+        uint32_t t = 0;
+        for (int k = 0; k < per_lane; k++) { const int i = lane * per_lane + k; if (i < per_warp) t += scnt[w0 + i]; }
+        uint32_t x = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) scur[BIG_BUCKETS_MAX + warp] = x;   // warp total (scratch behind the cursors)
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < warp; w++) base += scur[BIG_BUCKETS_MAX + w];
+        uint32_t e = base + x - t;
+        bool over = false;
+        for (int k = 0; k < per_lane; k++) {
+            const int i = lane * per_lane + k;
+            if (i < per_warp) {
+                const uint32_t c = scnt[w0 + i];
+                over |= c > (uint32_t)BIG_BUCKET_MAX;
+                scnt[w0 + i] = e; scur[w0 + i] = e; e += c;
+            }
+        }
+        if (over) sflags[2] = 1u;
+    }
+    __syncthreads();
+    if (sflags[2]) return false;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t k = gk[i];
+        gtmp[atomicAdd(&scur[bucket_of(k)], 1u)] = k;
+    }
+    __syncthreads();                                        // (block-scope: the CTA's global writes are visible to it)
+#pragma unroll 2
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t mine = gtmp[i];
+        const int bkt = bucket_of(mine);
+        const int first = (int)scnt[bkt], end = (int)scur[bkt];
+        int rank = 0;
+        for (int j = first; j < end; j++) rank += gtmp[j] < mine;
+        gk[first + rank] = mine;
+    }
+    __syncthreads();
+    return true;
+}
+
 // Sorts tile `tile`'s bucket (in shared memory when it fits, else in place in global memory) and
 // returns a pointer to the sorted keys; n = bucket size.  All threads of the CTA must call it.
 // skeys: SORT_SMEM_CAP keys of shared memory; bs: scratch of the bucketed path.
+// gtmp: n words of global scratch for large tiles (the callers pass the tile's own, not yet written, record plane).
 __device__ __forceinline__ const uint64_t* sort_tile_bucket(uint64_t* __restrict__ gk, int n, uint64_t* skeys,
-                                                            BucketSortSmem& bs, bool force_bitonic = false) {
+                                                            BucketSortSmem& bs, uint64_t* __restrict__ gtmp,
+                                                            bool force_bitonic = false) {
     if (n > 32 && n <= BUCKET_SORT_CAP && !force_bitonic) {
         uint64_t* a = skeys;
         uint64_t* b = skeys + BUCKET_SORT_CAP;
@@ -152,6 +242,14 @@ __device__ __forceinline__ const uint64_t* sort_tile_bucket(uint64_t* __restrict
         __syncthreads();
         bitonic_sort<true>(a, n, m);
         return a;
+    }
+    if (n > BUCKET_SORT_CAP && !force_bitonic && gtmp != nullptr) {
+        // large tile: bucketed sort through global memory; the 32 KB of skeys[] hold the bucket counters / cursors / flags
+        uint32_t* scnt = reinterpret_cast<uint32_t*>(skeys);
+        uint32_t* scur = scnt + BIG_BUCKETS_MAX;            // + 32 words of warp totals behind it
+        uint32_t* sflags = scur + BIG_BUCKETS_MAX + 32;
+        if (bucket_sort_global(gk, gtmp, n, scnt, scur, sflags)) return gk;
+        __syncthreads();                                    // degenerate distribution: the bitonic paths below (gk intact)
     }
     int m = 1;
     while (m < n) m <<= 1;

@@ -70,12 +70,14 @@ def test_product_matches_oracle(P, W, H, sh, seed):
     assert_grads_close(out["grads"], orc["grads"], grad_keys({}, sc))
 
 
-@pytest.mark.parametrize("mode", ["equal_depth", "two_depths", "one_outlier"])
-def test_degenerate_depth_distributions_keep_the_reference_order(mode):
+@pytest.mark.parametrize("mode,P", [("equal_depth", 6000), ("two_depths", 6000), ("one_outlier", 6000),
+                                    ("equal_depth", 40000), ("one_outlier", 40000)])
+def test_degenerate_depth_distributions_keep_the_reference_order(mode, P):
     """The per-tile sort partitions by depth buckets: all-equal depths (one bucket, ties resolved by index exactly like
     the reference's stable radix sort), two depth values and a single far outlier (all keys but one in one bucket) must
-    take the fallback path and still match the oracle."""
-    W, H, P = 96, 64, 6000
+    take the fallback path and still match the oracle.  P = 40 000 puts ~3 000 entries into every tile: the large-tile
+    (global-memory) bucketed sort and ITS fallback."""
+    W, H = 96, 64
     sc = synth.make_scene(P, W, H, seed=31, sigma_px=3.0, bg=(0.1, 0.2, 0.3))       # identity camera: view z == world z
     z = sc.means3D[:, 2].copy()
     if mode == "equal_depth":
