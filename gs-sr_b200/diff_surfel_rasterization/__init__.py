@@ -163,8 +163,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         grad_means2D, grad_colors, grad_opac = out(P, 3), out(P, 3), out(P, 1)
         grad_means3D, grad_tm, grad_normal = out(P, 3), out(P, 9), out(P, 3)
         grad_sh = torch.zeros((P, M, 3), dtype=torch.float32, device=dev) if sh_c.numel() == 0 else out(P, M, 3)
-        grad_scales, grad_rot = torch.zeros((P, 2), dtype=torch.float32, device=dev), \
-            torch.zeros((P, 4), dtype=torch.float32, device=dev)
+        # surfel_preprocess_bwd writes every row of both (zeros for culled Gaussians and with a precomputed transMat)
+        grad_scales, grad_rot = out(P, 2), out(P, 4)
         if P != 0:
             with _on_device(dev):
                 check(lib().gsr_surfel_backward(
