@@ -6,13 +6,10 @@ stream is capturing, a forward records every kernel once, laid out for ``capture
 ``num_rendered`` history of earlier eager calls of the same (device, rasterizer, resolution), and returns without
 waiting.  Typical use (a fixed-size training iteration -- between two densification steps of GS-SR's trainer)::
 
-    for _ in range(3):                       # eager warm-up: num_rendered history, allocator, optimizer state
-        step()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        step()                               # forward + loss + backward + optimizer.step() of capturable optimizers
-    for _ in range(n):
-        g.replay()
+    from gsr_b200.graphs import capture, capture_overflow
+    graph, loss = capture(step, warmup=3, before_capture=lambda: optimizer.zero_grad(set_to_none=True))
+    for _ in range(n):                       # step = forward + loss + backward + optimizer.step() (capturable=True)
+        graph.replay()
     torch.cuda.synchronize()
     if capture_overflow():                   # a replay's num_rendered outgrew the captured capacity
         ...                                  # frame was truncated: raise the margin / warm up again and re-capture
@@ -35,3 +32,28 @@ def capture_overflow(reset: bool = True) -> int:
     not fit (``PREFILTERED_VIOLATION`` for a `prefiltered` violation).  Call it after the replays have completed, from
     the thread that captured the graph."""
     return int(lib().gsr_capture_overflow(1 if reset else 0))
+
+
+def capture(step, warmup: int = 3, before_capture=None):
+    """Record ``step()`` into a CUDA graph the way the rasterizers need it: ``warmup`` eager calls on a side stream first
+    (they give every (rasterizer, resolution) its ``num_rendered`` history and let the allocator / optimizer reach their
+    steady state), then one captured call.  ``before_capture()`` runs between the two (typically
+    ``optimizer.zero_grad(set_to_none=True)``: gradients allocated during capture live in the graph's pool and are
+    overwritten, not accumulated, by every replay).  Returns ``(graph, result of the captured step())``; the result's
+    tensors are static and hold the outputs of the latest ``graph.replay()``."""
+    import torch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(max(int(warmup), 1)):
+            if before_capture is not None:
+                before_capture()
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    if before_capture is not None:
+        before_capture()
+    capture_overflow(reset=True)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        result = step()
+    return graph, result

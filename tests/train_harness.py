@@ -212,18 +212,8 @@ class MiniTwoDGSTrainer:
     def capture(self, warmup=3):
         """Eager warm-up on a side stream (num_rendered history, allocator, optimizer state), then one captured
         iteration.  Returns (graph, static loss tensor); every graph.replay() is one training iteration."""
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self.optimizer.zero_grad(set_to_none=True)
-                self.step_device()
-        torch.cuda.current_stream().wait_stream(side)
-        self.optimizer.zero_grad(set_to_none=True)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss = self.step_device()
-        return graph, loss
+        from gsr_b200.graphs import capture
+        return capture(self.step_device, warmup=warmup, before_capture=lambda: self.optimizer.zero_grad(set_to_none=True))
 
 
 class MiniScaffold2DGSTrainer(MiniTwoDGSTrainer):
