@@ -173,7 +173,7 @@ __device__ __forceinline__ float4 quat_vjp(float4 q, float3 v0, float3 v1, float
 
 // One thread per Gaussian; every output row is written (zeros when radii == 0).
 #ifndef GSR_PREBWD_MINB
-#define GSR_PREBWD_MINB 3      // 85 registers, 3 CTAs/SM: 132 -> 125 us at cfg-B (4 spills: 144 us)
+#define GSR_PREBWD_MINB 2      // with every load issued up front: 2 CTAs/SM (no spills) 117 us, 3 (108 B of spills) 120 us at cfg-B
 #endif
 __global__ void __launch_bounds__(256, GSR_PREBWD_MINB)
 surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
@@ -207,13 +207,23 @@ surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
 #pragma unroll
     for (int i = 0; i < 9; i++) dTout[i] = dT[i];
     const bool visible = radii[idx] > 0;
+    // every per-Gaussian load of the kernel is issued here, before the first use and regardless of visibility (rows of
+    // culled Gaussians are in bounds and ignored): one memory round trip instead of three dependent ones
+    const GeomRec g = geom[idx];
+    float3 p = make_float3(0.f, 0.f, 0.f);
+    float2 sc = make_float2(0.f, 0.f);
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (!precomp) {
+        p = make_float3(__ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1), __ldg(means3D + 3 * idx + 2));
+        q = __ldg(rotations + idx);
+        sc = __ldg(scales + idx);
+    }
     float view[16];
     load16(vc.view, view);
     // dL/dsh and the view-direction term of dL/dmean3D are produced by sh_backward_kernel (sh.cu), which runs
     // after this kernel and accumulates into dL_dmean3D
     (void)dL_dsh; (void)shs; (void)clamped; (void)D; (void)M;
     if (visible) {
-        GeomRec g = geom[idx];
         {   // moments of dL/dp -> dL/dT (the linear part of S/backward.cu:413-421, once per Gaussian)
             const float sx = moment_origin(g.tu.w, vc.W), sy = moment_origin(g.tv.w, vc.H);
             const float3 tw = make_float3(g.tw.x, g.tw.y, g.tw.z);
@@ -236,10 +246,8 @@ surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
 #pragma unroll
             for (int i = 0; i < 9; i++) dTout[i] = dT[i];
         }
-        float3 Tu, Tv, Tw, c0, c1, c2, normal = make_float3(0.f, 0.f, 0.f), p;
+        float3 Tu, Tv, Tw, c0, c1, c2, normal = make_float3(0.f, 0.f, 0.f);
         float Pm[3][4];
-        float2 sc = make_float2(0.f, 0.f);
-        float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
         if (precomp) {
             Tu = make_float3(g.tu.x, g.tu.y, g.tu.z);
             Tv = make_float3(g.tv.x, g.tv.y, g.tv.z);
@@ -247,9 +255,6 @@ surfel_preprocess_bwd(int P, int D, int M, const float* __restrict__ means3D,
         } else {
             // re-evaluated with scale_modifier ignored and Wb/Hb from float truncation
             // (S/backward.cu:484-512,614-615)
-            p = make_float3(__ldg(means3D + 3 * idx), __ldg(means3D + 3 * idx + 1), __ldg(means3D + 3 * idx + 2));
-            q = __ldg(rotations + idx);
-            sc = __ldg(scales + idx);
             quat_to_rot(q, c0, c1, c2);
             float3 L0 = make_float3(c0.x * sc.x, c0.y * sc.x, c0.z * sc.x);
             float3 L1 = make_float3(c1.x * sc.y, c1.y * sc.y, c1.z * sc.y);
