@@ -194,6 +194,53 @@ def test_bucketed_tile_sort_gives_the_bitonic_order():
     assert np.array_equal(a["radii"], b["radii"])
 
 
+@pytest.mark.parametrize("case", ["shell", "thin_shell", "heavy_shell", "two_shells"])
+def test_surface_like_depth_distributions_sort_like_the_bitonic_network(case):
+    """Most splats of a tile in a thin depth shell (a surface), a few spread over the frustum: the linear depth buckets of
+    the per-tile sort overflow and the equalised partition takes over (tile_sort.cuh) -- in shared memory for ordinary
+    tiles, through global memory for a tile of 6 000 entries.  (depth bits, index) keys are unique, so the result must be
+    bit-identical to the bitonic network's (dbg bit 0), which the other tests pin to the oracle / reference."""
+    import gsr_b200
+    rng = np.random.default_rng(7)
+    if case == "heavy_shell":
+        W = H = 64
+        P = 6000
+        sc = synth.make_scene(P, W, H, seed=95, sigma_px=1.2)
+        z = sc.means3D[:, 2].astype(np.float64)
+        znew = np.where(rng.random(P) < 0.97, 5.0 + rng.normal(0.0, 0.004, P), z)
+        f = 1.2 * W
+        u, v = rng.uniform(22.0, 26.0, P), rng.uniform(22.0, 26.0, P)      # all centres in the middle of tile (1, 1)
+        sc.means3D[:, 0] = ((u - W / 2) * znew / f).astype(np.float32)
+        sc.means3D[:, 1] = ((v - H / 2) * znew / f).astype(np.float32)
+        sc.means3D[:, 2] = znew.astype(np.float32)
+        sc.scales *= (znew / z).astype(np.float32)[:, None]
+        sc.opacities[:] = rng.uniform(0.01, 0.03, (P, 1)).astype(np.float32)
+    else:
+        W, H, P = 640, 400, 300_000
+        sc = synth.make_scene(P, W, H, seed=96)
+        z = sc.means3D[:, 2].astype(np.float64)
+        if case == "two_shells":
+            centre = np.where(rng.random(P) < 0.5, 4.0, 9.0)
+            znew = np.where(rng.random(P) < 0.96, centre + rng.normal(0.0, 0.01, P), z)
+        else:
+            znew = np.where(rng.random(P) < 0.95, 6.0 + rng.normal(0.0, 0.02 if case == "shell" else 0.0005, P), z)
+        k = (znew / z).astype(np.float32)
+        sc.means3D[:, 0] *= k; sc.means3D[:, 1] *= k; sc.means3D[:, 2] = znew.astype(np.float32)
+        sc.scales *= k[:, None]
+    gc, go = synth.make_upstream_grads(W, H, seed=97)
+    tt = hz.to_torch(sc)
+    out = hz.run_product_surfel(sc, gc, go, tt=tt)
+    gsr_b200.lib().gsr_set_option(b"dbg", 1)
+    try:
+        ref = hz.run_product_surfel(sc, gc, go, tt=tt)
+    finally:
+        gsr_b200.lib().gsr_set_option(b"dbg", 0)
+    assert np.isfinite(out["color"]).all() and out["others"][1].max() > 0.5
+    assert np.array_equal(out["color"], ref["color"]) and np.array_equal(out["others"], ref["others"])
+    for k_ in ("opacities", "colors", "means3D"):
+        assert np.abs(out["grads"][k_] - ref["grads"][k_]).max() <= 1e-5 * np.abs(ref["grads"][k_]).max()
+
+
 @pytest.mark.parametrize("P", [3000, 12000])
 def test_heavy_tiles_take_the_large_sort_paths(P):
     """Thousands of low-opacity splats stacked on ONE tile: its list has > 2048 entries (shared-memory bitonic network,
