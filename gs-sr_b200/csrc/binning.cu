@@ -115,7 +115,7 @@ scatter_keys(int P, const float* __restrict__ centre_x, const float* __restrict_
              const CullRec* __restrict__ cull,
              const float* __restrict__ depths, const int* __restrict__ radii, const uint32_t* __restrict__ masks, int gx, int gy,
              uint32_t* __restrict__ cursors, uint64_t* __restrict__ keys, uint32_t cap) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = spread_gaussian_index();
     const int lane = threadIdx.x & 31;
     const bool in_range = idx < P;
     const int li = in_range ? idx : P - 1;           // out-of-range lanes of the last warp load a valid row and ignore it
@@ -168,15 +168,58 @@ scatter_keys(int P, const float* __restrict__ centre_x, const float* __restrict_
         for (int u = 0; u < 4; u++)
             if (ok[u] && pos[u] < cap) keys[pos[u]] = ((uint64_t)khi[u] << 32) | klo[u];
     }
+    // ---- rectangles without a mask: the tile test is repeated, flattened over the CTA ----
+    // (a per-thread loop over a screen-filling splat's thousands of tiles was a 3 ms tail with 50 such splats among 500 k)
+    __shared__ float4 s_big[5][256];          // CullRec q0, q1 | sx, sy, mode, cx | cy, x0, y0, w | key lo, key hi
+    __shared__ int s_prefix[257];
+    __shared__ int s_wsum[8];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (!__syncthreads_or(retest)) return;
+    const int area_big = retest ? w * (y1 - y0) : 0;
     if (retest) {
-        const uint64_t key = ((uint64_t)dbits << 32) | (uint32_t)idx;
         const CullRec cr = cull[idx];
-        for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++)
-                if (tile_may_contribute(cr, cx, cy, x, y)) {
-                    const uint32_t pos = atomicAdd(&cursors[(size_t)(y * gx + x) * TILE_CTR_STRIDE], 1u);
-                    if (pos < cap) keys[pos] = key;
-                }
+        s_big[0][tid] = cr.q0;
+        s_big[1][tid] = cr.q1;
+        s_big[2][tid] = make_float4(cr.q2.x, cr.q2.y, cr.q2.z, cx);
+        s_big[3][tid] = make_float4(cy, __int_as_float(x0), __int_as_float(y0), __int_as_float(w));
+        s_big[4][tid] = make_float4(__uint_as_float((uint32_t)idx), __uint_as_float(dbits), 0.f, 0.f);
+    }
+    int bincl = area_big;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, bincl, o);
+        if (lane >= o) bincl += y;
+    }
+    if (lane == 31) s_wsum[warp] = bincl;
+    __syncthreads();
+    int wbase = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) wbase += k < warp ? s_wsum[k] : 0;
+    s_prefix[tid] = wbase + bincl - area_big;
+    if (tid == 255) s_prefix[256] = wbase + bincl;
+    __syncthreads();
+    const int btotal = s_prefix[256];
+    for (int base = 0; base < btotal; base += 256) {
+        const int t = base + tid;
+        if (t < btotal) {
+            int o = 0;                                     // the last thread whose exclusive prefix is <= t
+#pragma unroll
+            for (int step = 128; step > 0; step >>= 1)
+                if (s_prefix[o + step] <= t) o += step;
+            const int k = t - s_prefix[o];
+            CullRec r;
+            r.q0 = s_big[0][o];
+            r.q1 = s_big[1][o];
+            const float4 a = s_big[2][o], b = s_big[3][o], kk = s_big[4][o];
+            r.q2 = make_float4(a.x, a.y, a.z, 0.f);
+            const int rw = __float_as_int(b.w);
+            const int ry = k / rw, rx = k - ry * rw;
+            const int tx = __float_as_int(b.y) + rx, ty = __float_as_int(b.z) + ry;
+            if (tile_may_contribute(r, a.w, b.x, tx, ty)) {
+                const uint32_t pos = atomicAdd(&cursors[(size_t)(ty * gx + tx) * TILE_CTR_STRIDE], 1u);
+                if (pos < cap) keys[pos] = ((uint64_t)__float_as_uint(kk.y) << 32) | __float_as_uint(kk.x);
+            }
+        }
     }
 }
 

@@ -143,6 +143,13 @@ struct ViewParams {
 
 // ---- small device math ------------------------------------------------------
 #ifdef __CUDACC__
+// Gaussian handled by this thread in the per-Gaussian binning kernels (256 threads per CTA): warp w of CTA b takes the 32
+// CONSECUTIVE Gaussians of global warp w * gridDim.x + b, so loads stay coalesced while a contiguous run of big splats
+// (e.g. the children a densification step appends at the end of the arrays) is spread over as many CTAs as it has
+// warps -- with thread i <-> Gaussian i, 500 screen-filling splats in a row were the work of two CTAs (2.4 ms).
+__device__ __forceinline__ int spread_gaussian_index() {
+    return (int)(((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u));
+}
 __device__ __forceinline__ float3 xform43(const float* __restrict__ m, float3 p) {
     return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
                        m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],

@@ -236,4 +236,55 @@ __device__ __forceinline__ uint32_t warp_count_tiles(const CullRec& cr, float cx
     return s_mask[lane];
 }
 
+// ---- CTA-cooperative tile counting of BIG rectangles ---------------------------------------------
+// A screen-filling background / sky splat has thousands of tiles in its rectangle; inside the warp's list it kept ONE
+// warp busy for hundreds of rounds (50 such splats among 500 k: preprocess 56 us -> 1.7 ms).  Rectangles of more than
+// WARP_AREA_MAX tiles are therefore left out of the warp's list (area 0 there) and flattened over the whole 256-thread
+// CTA: block-wide prefix of their areas, item base + thread per round, owner by binary search over the prefix in shared
+// memory, the owner's record out of the s_rec rows warp_count_tiles has already written.  They never have a tile mask
+// (> 32 tiles), only counts.  All threads of the CTA must call it; CTAs without a big rectangle leave after one barrier.
+constexpr int WARP_AREA_MAX = 64;
+__device__ __forceinline__ void cta_count_big_tiles(int area_big, int gx, uint32_t* __restrict__ tile_count,
+                                                    float4 (*s_rec)[4][32], int* s_prefix /* [257] */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!__syncthreads_or(area_big > 0)) return;          // (also orders every warp's s_rec writes before the reads below)
+    int incl = area_big;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    __shared__ int s_wsum[8];
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) wbase += w < warp ? s_wsum[w] : 0;
+    s_prefix[tid] = wbase + incl - area_big;
+    if (tid == 255) s_prefix[256] = wbase + incl;
+    __syncthreads();
+    const int total = s_prefix[256];
+    for (int base = 0; base < total; base += 256) {
+        const int t = base + tid;
+        if (t < total) {
+            int o = 0;                                     // the last thread whose exclusive prefix is <= t
+#pragma unroll
+            for (int step = 128; step > 0; step >>= 1)
+                if (s_prefix[o + step] <= t) o += step;
+            const int k = t - s_prefix[o];
+            const int ow_ = o >> 5, ol = o & 31;
+            CullRec r;
+            r.q0 = s_rec[ow_][0][ol];
+            r.q1 = s_rec[ow_][1][ol];
+            const float4 a = s_rec[ow_][2][ol], b = s_rec[ow_][3][ol];
+            r.q2 = make_float4(a.x, a.y, a.z, 0.f);
+            const int rw = __float_as_int(b.w);
+            const int ry = k / rw, rx = k - ry * rw;
+            const int tx = __float_as_int(b.y) + rx, ty = __float_as_int(b.z) + ry;
+            if (tile_may_contribute(r, a.w, b.x, tx, ty))
+                atomicAdd(&tile_count[(size_t)(ty * gx + tx) * TILE_CTR_STRIDE], 1u);
+        }
+    }
+}
+
 }  // namespace gsr

@@ -82,7 +82,7 @@ __device__ __forceinline__ EwaProj ewa_project(float3 pv, float fx, float fy, fl
 
 // kRadiiOnly: scaffold_filter.visible_filter (F/forward.cu:267-342) -- stops at the radius.
 template <bool kRadiiOnly>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 ewa_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D, const float* __restrict__ scales,
                    const float4* __restrict__ rotations, const float* __restrict__ opacities,
                    const float* __restrict__ shs, const float* __restrict__ cov3D_precomp, const bool has_colors,
@@ -91,9 +91,10 @@ ewa_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D, const
                    EwaGeom* __restrict__ geom, CullRec* __restrict__ cull, float* __restrict__ depths,
                    uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_count, float* __restrict__ rgb,
                    uint8_t* __restrict__ clamped, int* __restrict__ flags) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = kRadiiOnly ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : spread_gaussian_index();
     __shared__ float4 s_rec[kRadiiOnly ? 1 : 8][4][32];      // warp_count_tiles (cull.cuh); unused by the radii-only filter
     __shared__ uint32_t s_mask[kRadiiOnly ? 1 : 8][32];
+    __shared__ int s_prefix[kRadiiOnly ? 1 : 257];       // cta_count_big_tiles
     int radius_out = 0;
     float view[16];
     load16(vc.view, view);
@@ -182,8 +183,10 @@ ewa_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D, const
     // tiles of the reference rect (G/auxiliary.h:46-56) the splat can actually reach, counted by the whole warp over
     // the flattened (Gaussian, tile) list (cull.cuh)
     const int wic = threadIdx.x >> 5;
-    const uint32_t m = warp_count_tiles(cr_t, cx_t, cy_t, x0_t, y0_t, w_t, area_t, vc.gx, tile_count,
+    const bool big = area_t > WARP_AREA_MAX;            // screen-filling rectangles: flattened over the CTA instead
+    const uint32_t m = warp_count_tiles(cr_t, cx_t, cy_t, x0_t, y0_t, w_t, big ? 0 : area_t, vc.gx, tile_count,
                                         s_rec[kRadiiOnly ? 0 : wic], s_mask[kRadiiOnly ? 0 : wic]);
+    if (!kRadiiOnly) cta_count_big_tiles(big ? area_t : 0, vc.gx, tile_count, s_rec, s_prefix);
     if (idx < P) {
         radii[idx] = radius_out;
         masks[idx] = area_t == 0 ? 0u : (area_t <= 32 ? m : MASK_RETEST);

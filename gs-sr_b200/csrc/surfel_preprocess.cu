@@ -52,7 +52,10 @@ __device__ __forceinline__ void aabb_row_pinned(float3 T, float3 Tw, float f0, f
     h2 = __fmaf_rn(c, c, nd);
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef GSR_PREFWD_MINB
+#define GSR_PREFWD_MINB 5      // 48 registers: 155 -> 149 us at cfg-B
+#endif
+__global__ void __launch_bounds__(256, GSR_PREFWD_MINB)
 surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
                       const float2* __restrict__ scales, const float4* __restrict__ rotations,
                       const float* __restrict__ opacities, const float* __restrict__ shs,
@@ -63,7 +66,8 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
                       uint8_t* __restrict__ clamped, int* __restrict__ flags) {
     __shared__ float4 s_rec[8][4][32];        // warp_count_tiles: the CullRec + rectangle of each lane, per warp
     __shared__ uint32_t s_mask[8][32];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_prefix[257];             // cta_count_big_tiles
+    const int idx = spread_gaussian_index();
     int radius_out = 0;
     float view[16];
     load16(vc.view, view);
@@ -152,7 +156,10 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
     // tiles of the reference rect (S/auxiliary.h:69-79) that the splat can actually reach: counted per tile (bucket
     // sizes) and remembered as a bit mask -- by the whole warp over the flattened (Gaussian, tile) list (cull.cuh)
     const int wic = threadIdx.x >> 5;
-    const uint32_t m = warp_count_tiles(cr_t, cx_t, cy_t, x0_t, y0_t, w_t, area_t, vc.gx, tile_count, s_rec[wic], s_mask[wic]);
+    const bool big = area_t > WARP_AREA_MAX;            // screen-filling rectangles: flattened over the CTA instead
+    const uint32_t m = warp_count_tiles(cr_t, cx_t, cy_t, x0_t, y0_t, w_t, big ? 0 : area_t, vc.gx, tile_count, s_rec[wic],
+                                        s_mask[wic]);
+    cta_count_big_tiles(big ? area_t : 0, vc.gx, tile_count, s_rec, s_prefix);
     if (idx < P) {
         radii[idx] = radius_out;
         masks[idx] = area_t == 0 ? 0u : (area_t <= 32 ? m : MASK_RETEST);

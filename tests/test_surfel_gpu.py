@@ -272,6 +272,29 @@ def test_heavy_tiles_take_the_large_sort_paths(P):
     assert np.array_equal(alt["color"], out["color"]) and np.array_equal(alt["others"], out["others"])
 
 
+@pytest.mark.parametrize("contiguous", [False, True])
+def test_screen_filling_splats_among_ordinary_ones(contiguous):
+    """Background / sky splats whose getRect rectangle covers hundreds of tiles: they have no tile mask, their tile test
+    is flattened over the CTA in the preprocess and in the scatter (cull.cuh, binning.cu).  Random indices and one
+    contiguous run (the children a densification step appends), against the reference build (or the oracle)."""
+    from oracle import refcuda
+    W, H, P, n_big = 640, 400, 40_000, 300
+    sc = synth.make_scene(P, W, H, seed=61)
+    rng = np.random.default_rng(62)
+    sel = np.arange(P - n_big, P) if contiguous else rng.choice(P, n_big, replace=False)
+    f = 1.2 * W
+    sig = rng.choice([25.0, 80.0, 250.0], n_big)                      # rectangles of ~100 tiles up to the whole 40 x 25 grid
+    sc.scales[sel] = (sig * sc.means3D[sel, 2] / f)[:, None].astype(np.float32) * rng.uniform(0.3, 1.0, (n_big, 2)).astype(np.float32)
+    sc.opacities[sel] = rng.uniform(0.02, 0.2, (n_big, 1)).astype(np.float32)
+    gc, go = synth.make_upstream_grads(W, H, seed=63)
+    tt = hz.to_torch(sc)
+    out = hz.run_product_surfel(sc, gc, go, tt=tt)
+    ref = hz.run_refcuda_surfel(sc, gc, go, tt=tt) if refcuda.available("surfel") else hz.run_oracle_surfel(sc, gc, go)
+    assert (out["radii"][sel] > 32).sum() > 0.8 * n_big
+    assert_forward_close(out, ref)
+    assert_grads_close(out["grads"], ref["grads"], grad_keys({}, sc))
+
+
 def test_image_with_more_than_8192_tiles():
     """2560x1440 = 160 x 90 = 14 400 tiles: tile_scan's chunks exceed its register-resident size (8 tiles per thread) and
     take the generic path; large and small splats, compared with the reference build (or the oracle without it)."""
