@@ -27,6 +27,7 @@ namespace gsr {
 
 constexpr int KNN_LEAF = 32;                 // points per leaf, children per internal node
 constexpr int KNN_MAX_LEVELS = 8;            // 32^7 leaves > 2^31 points
+constexpr int KNN_MOMENT_STRIDE = 8;         // sampling stride of the robust-box moments (large clouds)
 constexpr int RADIX_ITEMS = 8;               // keys per thread
 constexpr int RADIX_THREADS = 256;
 constexpr int RADIX_TILE = RADIX_ITEMS * RADIX_THREADS;
@@ -39,7 +40,7 @@ struct KnnLevels {
 };
 
 struct KnnWs {
-    uint32_t* bbox;      // [0..2] encoded min, [4..6] encoded max
+    uint32_t* bbox;      // [0..2] encoded min, [4..6] encoded max, [8..] moment sums of the robust box (knn_moments, doubles)
     uint32_t *keys0, *keys1, *vals0, *vals1;
     uint32_t* hist;      // 256 x nblocks
     float4* spts;        // sorted points: xyz + original index bits
@@ -48,7 +49,7 @@ struct KnnWs {
         Carver c(base);
         const size_t n = P > 0 ? (size_t)P : 1;
         const size_t nblocks = (n + RADIX_TILE - 1) / RADIX_TILE;
-        w.bbox = c.take<uint32_t>(8);
+        w.bbox = c.take<uint32_t>(64);
         w.keys0 = c.take<uint32_t>(n); w.keys1 = c.take<uint32_t>(n);
         w.vals0 = c.take<uint32_t>(n); w.vals1 = c.take<uint32_t>(n);
         w.hist = c.take<uint32_t>(256 * nblocks + 1);
@@ -98,6 +99,63 @@ __global__ void __launch_bounds__(256) knn_bbox(int P, const float* __restrict__
     }
 }
 
+// ---- 1b. robust box for the Morton grid --------------------------------------------------------------
+// The Morton codes only ORDER the points (the hierarchy's boxes come from the coordinates, the search is exact), but the
+// order decides how tight those boxes are: with the 1024^3 grid laid over the plain bounding box, ONE far outlier -- every
+// SfM cloud has some -- collapses the whole cloud into a handful of cells and the search degenerates (1 M points in the
+// unit cube + one point at 1e4: 764 ms instead of 2.2; the reference: 1 s).  The grid is therefore laid over
+// mean +- 4 sigma of the points per axis, with sigma taken over the points within +- 3 sigma of a first estimate (two
+// moment passes), clipped to the bounding box; points outside land in the border cells.
+//   sums[pass][axis] = {count, sum d, sum d^2} (d = x - bounding-box centre) as DOUBLES at (double*)(bbox + 8) + 9 * pass
+//   + 3 * axis: with an outlier the variance is a difference of two numbers ~1e7 times larger than itself
+// PASS 0: moments of all points (about the bounding-box centre, for conditioning); PASS 1: of the points within +- 3 sigma
+// of the pass-0 estimate
+__device__ __forceinline__ bool knn_mean_sd(const uint32_t* __restrict__ bbox, int pass, int k, double& mean, double& sd) {
+    const double* sm = reinterpret_cast<const double*>(bbox + 8) + 9 * pass + 3 * k;
+    const double n = sm[0];
+    if (!(n >= 2.0)) return false;
+    mean = sm[1] / n;
+    const double var = sm[2] / n - mean * mean;
+    sd = var > 0.0 ? sqrt(var) : 0.0;
+    return sd > 0.0 && sd < 1e300;
+}
+template <int PASS>
+__global__ void __launch_bounds__(256) knn_moments(int P, const float* __restrict__ pts, uint32_t* __restrict__ bbox) {
+    float lo[3], hi[3], c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float bl = dec_ordered(bbox[k]), bh = dec_ordered(bbox[4 + k]);
+        c[k] = 0.5f * (bl + bh);
+        lo[k] = bl; hi[k] = bh;
+        double mean, sd;
+        if (PASS == 1 && knn_mean_sd(bbox, 0, k, mean, sd)) {
+            lo[k] = (float)((double)c[k] + mean - 3.0 * sd); hi[k] = (float)((double)c[k] + mean + 3.0 * sd);
+        }
+    }
+    double cnt[3] = {0., 0., 0.}, s1[3] = {0., 0., 0.}, s2[3] = {0., 0., 0.};
+    // every KNN_MOMENT_STRIDE-th point is enough for a grid range (and keeps the FP64 work negligible)
+    const int step = P > 65536 ? KNN_MOMENT_STRIDE : 1;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * step; i < P; i += gridDim.x * blockDim.x * step)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float v = __ldg(pts + 3 * (size_t)i + k);
+            if (v >= lo[k] && v <= hi[k]) { const double d = (double)v - (double)c[k]; cnt[k] += 1.0; s1[k] += d; s2[k] += d * d; }
+        }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cnt[k] += __shfl_xor_sync(FULL, cnt[k], o);
+            s1[k] += __shfl_xor_sync(FULL, s1[k], o);
+            s2[k] += __shfl_xor_sync(FULL, s2[k], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            double* sm = reinterpret_cast<double*>(bbox + 8) + 9 * PASS + 3 * k;
+            atomicAdd(sm + 0, cnt[k]); atomicAdd(sm + 1, s1[k]); atomicAdd(sm + 2, s2[k]);
+        }
+    }
+}
+
 // ---- 2. Morton codes (K/simple_knn.cu:46-75: 10 bits per axis) ---------------------------------------
 __device__ __forceinline__ uint32_t spread10(uint32_t x) {
     x &= 0x3ffu;
@@ -114,7 +172,16 @@ __global__ void __launch_bounds__(256) knn_morton(int P, const float* __restrict
     uint32_t code = 0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const float lo = dec_ordered(bbox[k]), hi = dec_ordered(bbox[4 + k]);
+        // grid range: mean +- 4 sigma of the trimmed moments (taken about the bounding-box centre), clipped to the box
+        const float bl = dec_ordered(bbox[k]), bh = dec_ordered(bbox[4 + k]);
+        float lo = bl, hi = bh;
+        {
+            double mean, sd;
+            if (knn_mean_sd(bbox, 1, k, mean, sd)) {
+                const double cc = 0.5 * ((double)bl + (double)bh);
+                lo = fmaxf(bl, (float)(cc + mean - 4.0 * sd)); hi = fminf(bh, (float)(cc + mean + 4.0 * sd));
+            }
+        }
         const float ext = hi - lo;
         const float t = ext > 0.f ? (__ldg(pts + 3 * (size_t)i + k) - lo) / ext : 0.f;
         const uint32_t q = (uint32_t)fminf(fmaxf(t * 1023.0f, 0.f), 1023.f);   // NaN -> 0
@@ -390,9 +457,11 @@ int gsr_dist2_knn3(int P, const float* points, float* meanDists, void* workspace
     char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     KnnWs::carve(w, base, P);
     GSR_CUDA_CHECK(cudaMemsetAsync(w.bbox, 0xff, 4 * sizeof(uint32_t), s));
-    GSR_CUDA_CHECK(cudaMemsetAsync(w.bbox + 4, 0, 4 * sizeof(uint32_t), s));
+    GSR_CUDA_CHECK(cudaMemsetAsync(w.bbox + 4, 0, 60 * sizeof(uint32_t), s));      // encoded max + the moment sums
     const int nb256 = (P + 255) / 256;
     knn_bbox<<<min(nb256, 148 * 8), 256, 0, s>>>(P, points, w.bbox);
+    knn_moments<0><<<min(nb256, 148 * 2), 256, 0, s>>>(P, points, w.bbox);
+    knn_moments<1><<<min(nb256, 148 * 2), 256, 0, s>>>(P, points, w.bbox);
     knn_morton<<<nb256, 256, 0, s>>>(P, points, w.bbox, w.keys0, w.vals0);
     const int nblocks = (P + RADIX_TILE - 1) / RADIX_TILE;
     uint32_t *ki = w.keys0, *vi = w.vals0, *ko = w.keys1, *vo = w.vals1;

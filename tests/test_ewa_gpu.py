@@ -287,6 +287,25 @@ def test_knn_product_matches_oracle_bit_exactly(P, clustered):
     assert np.array_equal(d.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("case", ["far_outlier", "two_outliers_and_duplicates", "slab"])
+def test_knn_with_outliers_matches_oracle_bit_exactly(case):
+    """SfM clouds have far outliers: the Morton grid is laid over a robust box (mean +- 4 sigma of trimmed moments, knn.cu),
+    points outside fall into the border cells.  The order is only a heuristic -- the result must stay the exact 3-NN."""
+    from oracle import oracle as orc
+    from simple_knn._C import distCUDA2
+    rng = np.random.default_rng(17)
+    pts = rng.random((30000, 3), dtype=np.float32)
+    if case == "far_outlier":
+        pts[123] = 1e4
+    elif case == "two_outliers_and_duplicates":
+        pts[5] = (-3e3, 2e3, 10.0); pts[6] = (4e3, -1e3, -2e3); pts[100:200] = pts[300]
+    else:
+        pts[:, 2] *= 1e-4; pts[7, 2] = 50.0
+    d = distCUDA2(torch.from_numpy(pts).cuda()).cpu().numpy()
+    want = orc.dist2_knn3(pts)
+    assert np.array_equal(d.view(np.uint32), want.view(np.uint32))
+
+
 def test_knn_full_size_properties():
     """2 M points: invariance under permutation of the input order (a size-independent property of an exact
     k-NN), bit-equality with the reference CUDA build when it travelled, degenerate axis."""
