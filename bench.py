@@ -465,7 +465,11 @@ def train_iters(impl):
         out["cuda_graph"] = {"unavailable": "the reference forward blocks on a cudaMemcpy of num_rendered "
                                             "(S/cuda_rasterizer/rasterizer_impl.cu:282): it cannot be captured"}
     for name, kw in (("config3_scaffold2dgs", dict(P=400_000, W=1600, H=1060, scaffold=True)),
-                     ("config4_pgsr", dict(P=1_000_000, W=1600, H=900, pgsr=True))):
+                     ("config4_pgsr", dict(P=1_000_000, W=1600, H=900, pgsr=True)),
+                     # the octree scene classes of BASELINE configs 4 / 5: anchors x 5 neural Gaussians behind the
+                     # level-of-detail mask and the octree prefilter (P = anchors)
+                     ("config4_octree_pgsr", dict(P=200_000, W=1600, H=900, pgsr=True, octree=True)),
+                     ("config5_octree_2dgs", dict(P=400_000, W=1600, H=1060, octree=True))):
         try:
             vv, _ = measure_iters_per_s(arm, iters=15, warmup=3, fused_ssim=ours, fused_post=ours, **kw)
             out[name] = {"value": vv, "unit": "iters/s"}
