@@ -5,14 +5,15 @@
 // exactly what the reference's stable radix sort of (tile << 32 | depth_bits) keys over pairs
 // emitted in ascending Gaussian index produces.  The reference sorts all R pairs globally
 // (6 radix passes over 12-byte pairs); here the tile is known when a pair is emitted, so
-//   1. the forward preprocess counts pairs per tile (atomicAdd on a tiles-sized histogram),
+//   1. the forward preprocess counts pairs per tile (atomicAdd on a tiles-sized histogram; the tile test runs on the
+//      warp's -- for big rectangles the CTA's -- flattened (Gaussian, tile) list, cull.cuh),
 //   2. tile_scan turns counts into per-tile offsets (one CTA; also yields R, published to the host through a
 //      pinned slot so that the host never blocks the stream to learn it, see abi.cu),
 //   3. scatter_keys drops each pair's 64-bit (depth_bits << 32 | index) key into its tile's
-//      bucket (slot order inside a bucket is arbitrary -- the key is a total order),
-//   4. sort_build_records: one CTA per tile sorts its bucket with a bitonic network in shared
-//      memory (global memory for oversized buckets) and, fused, materialises the tile-local
-//      record planes the render kernels stream (six float4 planes, coalesced stores).
+//      bucket (slot order inside a bucket is arbitrary -- the key is a total order), again over flattened lists,
+//   4. sort_build_records: one CTA per tile sorts its bucket (tile_sort.cuh: depth buckets + rank counting in shared
+//      memory, through global memory for tiles of more than 2048 entries, bitonic networks as the fallback) and,
+//      fused, materialises the tile-local record planes the render kernels stream (six float4 planes, coalesced stores).
 // A (Gaussian, tile) pair of the reference's getRect rectangle is only emitted when the splat
 // can reach alpha >= 1/255 somewhere in that tile (cull.cuh); dropped pairs are list entries
 // on which every pixel of the tile would `continue`.

@@ -8,10 +8,10 @@
 //
 // B200 design:
 //   * same warp/pixel mapping (8x4 pixels per warp), cp.async.bulk staging and exact warp-block
-//     culling as the forward, but one CTA = 4 warps = HALF a tile (16x8 pixels; two CTAs per
-//     tile walk the same list) and the warps of a CTA are decoupled: a ring whose stages are
+//     culling as the forward (one CTA = 8 warps = one tile; GSR_BWD_WARPS = 4 / 2 builds half-tile /
+//     strip CTAs that walk the same list), but the warps of a CTA are decoupled: a ring whose stages are
 //     refilled by whichever warp arrives last, no __syncthreads() in the walk; the walk starts
-//     at the half tile's last needed batch (max last_contributor);
+//     at the CTA's last needed batch (max last_contributor);
 //   * TWO PHASES per warp.  Phase 1 is pixel-parallel (lane = pixel) and sequential over the
 //     contributing splats, because the blend state (T and the "blended behind" recurrence) is a
 //     chain along the list: it turns one (pixel, splat) pair into six numbers -- dL/dp (3),

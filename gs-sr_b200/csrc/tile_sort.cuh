@@ -1,5 +1,7 @@
-// tile_sort.cuh -- per-tile bitonic sort of (depth_bits << 32 | index) keys, shared by the
-// record-building kernels of both rasterizer families (see binning.cu for the ordering contract).
+// tile_sort.cuh -- per-tile sort of (depth_bits << 32 | index) keys, shared by the record-building kernels of both
+// rasterizer families (see binning.cu for the ordering contract): a bucketed sort (linear depth buckets, refined by
+// histogram equalisation when a surface piles the keys up; rank counting per key) in shared memory for tiles of up to
+// 2048 entries and through global memory above, with the bitonic networks below as the fallback for coincident depths.
 #pragma once
 #include "common.cuh"
 
