@@ -80,6 +80,27 @@ def lib():
         L.gsr_tsdf_integrate_grid.restype = C.c_int
         L.gsr_tsdf_integrate_grid.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float, C.c_int, _fp,
                                                               C.c_int, _fp, _fp, _fp, C.c_void_p]
+    if hasattr(L, "gsr_mc_count"):
+        L.gsr_mc_workspace_bytes.restype = C.c_size_t
+        L.gsr_mc_workspace_bytes.argtypes = [C.c_int] * 3
+        L.gsr_mc_count.restype = C.c_int
+        L.gsr_mc_count.argtypes = [C.c_int] * 3 + [_fp, _fp, C.c_float, C.c_float, _fp, C.POINTER(C.c_longlong),
+                                                   C.POINTER(C.c_longlong), C.c_void_p]
+        L.gsr_mc_emit.restype = C.c_int
+        L.gsr_mc_emit.argtypes = [C.c_int] * 3 + [_fp, _fp, C.c_float, C.POINTER(C.c_float), C.c_float, _fp, _fp, _fp, _fp,
+                                                  C.c_void_p]
+    if hasattr(L, "gsr_mesh_clusters"):
+        _ll = C.c_longlong
+        L.gsr_mesh_clusters.restype = C.c_int
+        L.gsr_mesh_clusters.argtypes = [_ll, _ll] + [_fp] * 6 + [C.c_void_p]
+        L.gsr_mesh_keep_clusters.restype = C.c_int
+        L.gsr_mesh_keep_clusters.argtypes = [_ll, _fp, _fp, C.c_uint, _fp, C.c_void_p]
+        L.gsr_mesh_filter_workspace_bytes.restype = C.c_size_t
+        L.gsr_mesh_filter_workspace_bytes.argtypes = [_ll, _ll]
+        L.gsr_mesh_filter_count.restype = C.c_int
+        L.gsr_mesh_filter_count.argtypes = [_ll, _ll, _fp, _fp, _fp, C.POINTER(_ll), C.POINTER(_ll), C.c_void_p]
+        L.gsr_mesh_filter_emit.restype = C.c_int
+        L.gsr_mesh_filter_emit.argtypes = [_ll, _ll] + [_fp] * 7 + [C.c_void_p]
     if hasattr(L, "gsr_depth_normal_forward"):
         L.gsr_depth_normal_forward.restype = C.c_int
         L.gsr_depth_normal_forward.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_void_p]

@@ -149,7 +149,7 @@ class BoundedTSDFVolume:
         vol = BoundedTSDFVolume(origin, voxel_size, (nx, ny, nz), sdf_trunc, depth_trunc, with_rgb=True)
         vol.integrate(full_proj_transforms, depthmaps, rgbmaps)       # as often as views arrive
         vol.reduce_to(0)                                              # config 5: sum the per-tile volumes on rank 0
-        sdf = vol.tsdf                                                # (nz, ny, nx) lattice for marching cubes
+        mesh = vol.extract_triangle_mesh()                            # marching cubes on the GPU (gsr_b200.mesh)
 
     Lattice point (ix, iy, iz) = origin + (ix, iy, iz) * voxel_size; ``tsdf`` / ``weight`` are (nz, ny, nx), ``rgb``
     (nz, ny, nx, 3): the array layout marching-cubes implementations take (mcube_utils.py:57-68 reshapes its samples the
@@ -197,6 +197,18 @@ class BoundedTSDFVolume:
         if out is not None:
             self.tsdf, self.weight, self.rgb = out
         return self
+
+
+    @torch.no_grad()
+    def extract_triangle_mesh(self, level=0.0):
+        """``volume.extract_triangle_mesh()`` of the reference's bounded paths (mesh_utils.py:178,
+        extract_mesh_split.py:119): marching cubes over the cells whose eight corners were all observed (weight > 1, the
+        initial weight), vertex colours interpolated from ``rgb``.  Runs on this GPU (gsr_b200.mesh)."""
+        from .mesh import extract_triangle_mesh
+        if self._fresh:
+            self.integrate([], [], [] if self.rgb is not None else None)
+        org = [float(v) for v in self._origin]
+        return extract_triangle_mesh(self.tsdf, self.weight, 1.0, level, org, self.voxel_size, self.rgb)
 
 
 def reduce_partial_volume(tsdf, weight, rgb=None, dst=0, group=None):

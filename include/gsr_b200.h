@@ -311,6 +311,52 @@ int gsr_tsdf_integrate_grid(int nx, int ny, int nz, const float* origin_host3, f
                             float depth_trunc, int nviews, const gsr_tsdf_view* views, int init, float* tsdf,
                             float* weights, float* rgb, void* stream);
 
+/* Triangle mesh of the level set of a TSDF lattice (marching cubes): the step the reference hands its fused volume to --
+ * volume.extract_triangle_mesh() of Open3D's ScalableTSDFVolume (gssr/utils/mesh_utils.py:178, extract_mesh_split.py:119)
+ * and skimage.measure.marching_cubes(level=0) on host chunks (gssr/utils/mcube_utils.py:71-80).  Both are absent
+ * third-party dependencies: PARITY UNPINNED against them; conventions follow Open3D's extractor (inside = f < level; a cell
+ * yields triangles only when all eight corners have weight > min_weight; vertices at f0 / (f0 - f1) of a lattice edge, shared
+ * between cells; colours interpolated with the same weight) and the case table is consistent across cell faces, so closed
+ * surfaces come out closed.  Lattice as in gsr_tsdf_integrate_grid: (nz, ny, nx) floats, x fastest, point (ix, iy, iz) =
+ * origin + (ix, iy, iz) * voxel_size.  Two calls, the caller allocates in between:
+ *   gsr_mc_count   classifies the cells into `workspace` (gsr_mc_workspace_bytes(nx, ny, nz) device bytes, 256-byte aligned)
+ *                  and returns the vertex / triangle counts; weight == NULL = every corner counts.  Synchronises `stream`.
+ *   gsr_mc_emit    writes verts (nverts, 3) f32, colors (nverts, 3) f32 (iff rgb (nz, ny, nx, 3) is given) and faces (ntris, 3)
+ *                  i32 from the same tsdf / level / workspace.  Asynchronous.  Output order is lattice order: vertices by
+ *                  (owner voxel, axis), faces by (cell, table order), normals towards f > level -- deterministic.
+ * Lattices of 2^31 voxels or more, or meshes beyond 32-bit indices, return GSR_E_OVERFLOW: extract them in slabs. */
+size_t gsr_mc_workspace_bytes(int nx, int ny, int nz);
+int gsr_mc_count(int nx, int ny, int nz, const float* tsdf, const float* weight, float min_weight, float level,
+                 void* workspace, long long* nverts_host, long long* ntris_host, void* stream);
+int gsr_mc_emit(int nx, int ny, int nz, const float* tsdf, const float* rgb, float level, const float* origin_host3,
+                float voxel_size, const void* workspace, float* verts, float* colors, int* faces, void* stream);
+
+/* Mesh clean-up of GS-SR's post_process_mesh (gssr/utils/mesh_utils.py:27-49; Open3D cluster_connected_triangles /
+ * remove_triangles_by_mask / remove_unreferenced_vertices / remove_degenerate_triangles on the host; Open3D absent: PARITY
+ * UNPINNED, the steps are restated by oracle/mesh_clusters_oracle.py).
+ *   gsr_mesh_clusters       connected components (lock-free union-find over the vertices, one thread per triangle):
+ *                           vertex_root[v] = smallest vertex id of v's component, tri_root[t] = component of triangle t,
+ *                           root_ntris[r] / root_area[r] = triangles / area of the component whose smallest vertex is r
+ *                           (0 at every other index; root_area and verts may both be NULL).  Triangles are joined through
+ *                           shared vertices (Open3D: shared edges -- the same clusters unless two sheets touch in one point).
+ *                           Synchronises `stream`; GSR_E_INVALID if a triangle indexes outside [0, nverts).
+ *   gsr_mesh_keep_clusters  keep[t] = root_ntris[tri_root[t]] >= min_triangles  (mesh_utils.py:42: the inverse of
+ *                           triangles_to_remove).
+ *   gsr_mesh_filter_count / gsr_mesh_filter_emit   drop the triangles with tri_keep[t] == 0, then the vertices no kept triangle
+ *                           references, then triangles with a repeated index (the reference's order of calls); survivors
+ *                           keep their order.  count returns the new sizes (synchronises), the caller allocates, emit
+ *                           writes verts_out / colors_out (iff colors) / faces_out (re-indexed).  workspace:
+ *                           gsr_mesh_filter_workspace_bytes(nverts, ntris) device bytes, 256-byte aligned, shared by the two. */
+int gsr_mesh_clusters(long long nverts, long long ntris, const float* verts, const int* faces, int* vertex_root, int* tri_root,
+                      unsigned int* root_ntris, double* root_area, void* stream);
+int gsr_mesh_keep_clusters(long long ntris, const int* tri_root, const unsigned int* root_ntris, unsigned int min_triangles,
+                           unsigned char* tri_keep, void* stream);
+size_t gsr_mesh_filter_workspace_bytes(long long nverts, long long ntris);
+int gsr_mesh_filter_count(long long nverts, long long ntris, const int* faces, const unsigned char* tri_keep, void* workspace,
+                          long long* nverts_out_host, long long* ntris_out_host, void* stream);
+int gsr_mesh_filter_emit(long long nverts, long long ntris, const float* verts, const float* colors, const int* faces,
+                         const void* workspace, float* verts_out, float* colors_out, int* faces_out, void* stream);
+
 /* ---- fused SSIM loss (image-space step right after the rasterizer) ---------------------- */
 
 /* Replaces VanillaScene._ssim / .ssim (gssr/scene/vanilla_scene.py:32-61): five depthwise 11x11

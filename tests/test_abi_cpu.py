@@ -157,6 +157,29 @@ def test_tsdf_fuse_argument_validation_without_gpu():
     assert b"gsr_tsdf_fuse" in L.gsr_last_error()
 
 
+def test_mesh_entry_points_argument_validation_without_gpu():
+    import ctypes as C
+    import gsr_b200
+    L = gsr_b200.lib()
+    nv, nt = C.c_longlong(0), C.c_longlong(0)
+    assert L.gsr_mc_workspace_bytes(0, 4, 4) == 0
+    ws = L.gsr_mc_workspace_bytes(512, 512, 512)
+    assert 3 * 512 ** 3 < ws < 3.1 * 512 ** 3                       # 1 + 2 bytes per voxel + counters
+    assert L.gsr_mc_count(0, 4, 4, None, None, 0.0, 0.0, None, C.byref(nv), C.byref(nt), None) == -1
+    assert L.gsr_mc_count(4, 4, 4, None, None, 0.0, 0.0, None, C.byref(nv), C.byref(nt), None) == -1      # tsdf required
+    assert L.gsr_mc_count(2048, 2048, 2048, None, None, 0.0, 0.0, None, C.byref(nv), C.byref(nt), None) != 0
+    assert b"slabs" in L.gsr_last_error()
+    assert L.gsr_mc_emit(4, 4, 4, None, None, 0.0, None, 1.0, None, None, None, None, None) == -1
+    assert L.gsr_mesh_clusters(-1, 0, None, None, None, None, None, None, None) == -1
+    assert L.gsr_mesh_clusters(0, 0, None, None, None, None, None, None, None) == 0                          # nothing to do
+    assert L.gsr_mesh_clusters(3, 1, None, None, None, None, None, None, None) == -1
+    assert L.gsr_mesh_keep_clusters(0, None, None, 50, None, None) == 0
+    assert L.gsr_mesh_keep_clusters(5, None, None, 50, None, None) == -1
+    assert L.gsr_mesh_filter_workspace_bytes(1000, 2000) >= 1000 * 5 + 2000
+    assert L.gsr_mesh_filter_count(10, 10, None, None, None, C.byref(nv), C.byref(nt), None) == -1
+    assert L.gsr_mesh_filter_emit(10, 10, None, None, None, None, None, None, None, None) == -1
+
+
 def test_header_is_plain_c99():
     """The drop-in boundary is a C ABI: include/gsr_b200.h must compile as C (no C++, no torch / CUDA types) and a C
     program that links only against the shared library must resolve every declared symbol."""
