@@ -18,7 +18,7 @@ One JSON line on rank 0:
   step_ms: median / p10 / p90 of the K per-step event times (BASELINE.md's reporting protocol)
   evals  : K_eval (per tile 256 x list entries walked before the block exits, reference definition,
            counted by the CPU port on the full frame) and FP32 pair evaluations/s = K_eval / step time
-  extras : the other hot-path workloads (cfg-A surfel, 3DGS 1M, plane cfg-4, visible_filter 2M, distCUDA2 1M, SSIM loss, TSDF fusion), same
+  extras : the other hot-path workloads (cfg-A surfel, 3DGS 1M, plane cfg-4, visible_filter 2M, distCUDA2 1M, SSIM loss, TSDF fusion, mesh extraction), same
            timing for both arms (tests/bench_extras.py)
   train  : BASELINE's "train iters/s" on config 2, with the fused image-space ops and rasterizer-only
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
@@ -408,7 +408,8 @@ def cpu_oracle_full(P, W, H, stride=4):
 def mesh_gather_check(rank, world, device):
     """Config 5's one collective (extract_mesh_split.py:58-119): every rank fuses ITS tile's views into the same bounded
     TSDF lattice, the partial volumes are summed onto rank 0 with one NCCL reduce (gsr_b200.tsdf.BoundedTSDFVolume), and
-    rank 0 checks the result against fusing all ranks' views itself.  Returns the record on rank 0, None elsewhere."""
+    rank 0 checks the result against fusing all ranks' views itself, then meshes it on its GPU (gsr_b200.mesh: marching
+    cubes + cluster filter).  Returns the record on rank 0, None elsewhere."""
     import torch
     from gsr_b200.tsdf import BoundedTSDFVolume
     from tsdf_synth import build_tsdf_case
@@ -430,9 +431,18 @@ def mesh_gather_check(rank, world, device):
         return None
     every = [v for r in range(world) for v in ((2 * r) % nv, (2 * r + 1) % nv)]
     full = BoundedTSDFVolume(with_rgb=True, device=device, **grid).integrate(*pick(every))
+    # ... and meshes the gathered volume where it lies (extract_mesh_split.py:119-128: extract_triangle_mesh + post_process_mesh)
+    from gsr_b200.mesh import post_process_mesh
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    mesh = post_process_mesh(vol.extract_triangle_mesh(), cluster_to_keep=50)
+    m1.record(); torch.cuda.synchronize()
+    ref_mesh = post_process_mesh(full.extract_triangle_mesh(), cluster_to_keep=50)
     return {"voxels": 128 ** 3, "views": len(every), "reduce_ms": e0.elapsed_time(e1), "bytes_per_rank": 128 ** 3 * 20,
             "max_abs_err_tsdf": float((vol.tsdf - full.tsdf).abs().max()), "weights_equal": bool(torch.equal(vol.weight, full.weight)),
-            "max_abs_err_rgb": float((vol.rgb - full.rgb).abs().max())}
+            "max_abs_err_rgb": float((vol.rgb - full.rgb).abs().max()),
+            "mesh_ms": m0.elapsed_time(m1), "mesh_triangles": int(mesh.triangles.shape[0]),
+            "mesh_triangles_single_gpu_volume": int(ref_mesh.triangles.shape[0])}
 
 
 def train_iters(impl):

@@ -8,6 +8,9 @@ that every row of DESIGN.md's speed table comes out of a driver-run bench line:
   dist2_knn3       simple_knn distCUDA2 on 1M points
   ssim_loss        SSIM loss fwd+bwd, 3x1060x1600 (reference arm: the reference's conv2d formulation in torch, same GPU)
   tsdf_fuse        TSDF fusion, 256^3 samples x 32 views @ 1600x1060 (reference arm: the reference's per-view torch rule)
+  mesh_extract     marching cubes + cluster filter of a 512^3 TSDF lattice, all on the device (reference arm: Open3D /
+                   skimage are absent -- the numpy restatement oracle/mcubes_oracle.py + mesh_clusters_oracle.py on the host,
+                   kind "port", on a 128^3 crop after the device->host copy the reference's unbounded path makes)
 
 Each entry: {"ms": device time per call (CUDA events, inputs resident, median of the timed calls), "value": units/s,
 "unit": ...}.  Test/bench infrastructure: imports the drop-in packages for our arm and oracle/refcuda.py (ctypes front-end
@@ -217,6 +220,40 @@ def tsdf_fuse(impl, Ng=256):
     return _entry(ev_times(fn, n, w), pts.shape[0] * len(projs), "sample-views/s")
 
 
+def mesh_extract(impl, n=512):
+    """extract_triangle_mesh + post_process_mesh (mesh_utils.py:27-49,178; mcube_utils.py:71-80) of a bumpy sphere in a
+    n^3 lattice.  Units: lattice voxels per second through both steps."""
+    import torch
+    ax = torch.arange(n, device="cuda", dtype=torch.float32)
+    z, y, x = torch.meshgrid(ax, ax, ax, indexing="ij")
+    c = (n - 1) / 2
+    f = torch.sqrt((x - c) ** 2 + (y - c) ** 2 + (z - c) ** 2) - 0.35 * n
+    f = f + 3.0 * torch.sin(x * 0.21) * torch.sin(y * 0.17) * torch.sin(z * 0.13)
+    del x, y, z
+    if impl == "ours":
+        from gsr_b200.mesh import extract_triangle_mesh, post_process_mesh
+        fn = lambda: post_process_mesh(extract_triangle_mesh(f, voxel_size=0.01), cluster_to_keep=50)  # noqa: E731
+        out = _entry(ev_times(fn, 5, 2), n ** 3, "voxels/s")
+        m = extract_triangle_mesh(f, voxel_size=0.01)
+        out["triangles"] = int(m.triangles.shape[0])
+        return out
+    import time
+    from oracle import mcubes_oracle, mesh_clusters_oracle
+    k = 128
+    lo = (n - k) // 2
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        crop = f[lo:lo + k, lo:lo + k, :k].contiguous().cpu().numpy()           # the unbounded path's `.cpu().numpy()`
+        v, faces, _ = mcubes_oracle.extract(crop, voxel_size=0.01)
+        mesh_clusters_oracle.post_process_mesh(v, faces, None, cluster_to_keep=50)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    out = _entry(ts, k ** 3, "voxels/s")
+    out.update(kind="port", sample=f"{k}^3 crop of the {n}^3 lattice, numpy/scipy on the host", triangles=int(faces.shape[0]))
+    return out
+
+
 WORKLOADS = {
     "cfgA_surfel": (lambda impl: surfel_cfg_a(impl), "surfel"),
     "gauss_1m": (lambda impl: ewa(impl, False), "gaussian"),
@@ -226,6 +263,7 @@ WORKLOADS = {
     # the reference arm of the next two is the reference's own torch formulation (no oracle/_ref library involved)
     "ssim_loss": (lambda impl: ssim_loss(impl), None),
     "tsdf_fuse": (lambda impl: tsdf_fuse(impl), None),
+    "mesh_extract": (lambda impl: mesh_extract(impl), None),
 }
 
 

@@ -27,7 +27,8 @@ def _same(got, want):
             assert g.dtype == w.dtype and g.shape == w.shape and np.array_equal(g, w)
 
 
-@pytest.mark.parametrize("shape,seed", [((12, 13, 14), 0), ((33, 32, 31), 1), ((5, 70, 300), 2), ((130, 9, 11), 3), ((2, 2, 2), 4)])
+@pytest.mark.parametrize("shape,seed", [((12, 13, 14), 0), ((33, 32, 31), 1), ((5, 70, 300), 2), ((130, 9, 11), 3), ((2, 2, 2), 4),
+                                        ((3, 5, 7), 5), ((9, 33, 2), 6), ((64, 64, 64), 7)])
 def test_noise_fields_match_the_oracle_bit_for_bit(shape, seed):
     from oracle import mcubes_oracle as mc
     f = ms.noise(shape, seed)
