@@ -120,6 +120,44 @@ class TSDFFusion:
         return tsdfs
 
 
+    # ---- the rest of extract_mesh_unbounded (mesh_utils.py:187-193, 248-277) -------------------------------------
+    def _center_t(self):
+        return torch.tensor([float(v) for v in self._center], dtype=torch.float32, device=self.device)
+
+    def contract_normalized(self, x):
+        """``contract(normalize(x))`` (:187-189, :248)."""
+        y = (x.to(self.device, torch.float32) - self._center_t()) / self.radius
+        mag = torch.linalg.norm(y, ord=2, dim=-1)[..., None]
+        return torch.where(mag < 1, y, (2 - (1 / mag)) * (y / mag))
+
+    def inv_contraction(self, y):
+        """``unnormalize(uncontract(y))`` (:191-193, :249-250)."""
+        mag = torch.linalg.norm(y, ord=2, dim=-1)[..., None]
+        x = torch.where(mag < 1, y, (1 / (2 - mag) * (y / mag)))
+        return x * self.radius + self._center_t()
+
+    @torch.no_grad()
+    def extract_mesh_unbounded(self, resolution=1024, gaussians_xyz=None, crop=512):
+        """``GaussianExtractor.extract_mesh_unbounded`` (mesh_utils.py:181-277) with this object's views: TSDF on the
+        contracted lattice (gsr_tsdf_fuse), marching cubes on the GPU (gsr_b200.mesh.marching_cubes_with_contraction),
+        vertex colours from a second fusion pass at the vertices.  `gaussians_xyz`: the Gaussian centres that set the
+        lattice's half-width R (95 % quantile of their contracted norm, :259-261); None = 1.9, the cap."""
+        from .mesh import marching_cubes_with_contraction
+        N = int(resolution)
+        voxel_size = self.radius * 2 / N
+        R = 1.9
+        if gaussians_xyz is not None:
+            import numpy as np
+            q = np.quantile(self.contract_normalized(gaussians_xyz).norm(dim=-1).cpu().numpy(), q=0.95)
+            R = min(float(q) + 0.01, 1.9)
+        mesh = marching_cubes_with_contraction(lambda x: self.compute_unbounded_tsdf(x, True, voxel_size), resolution=N,
+                                               bounding_box_min=(-R, -R, -R), bounding_box_max=(R, R, R), level=0.0,
+                                               inv_contraction=self.inv_contraction, crop=crop, device=self.device)
+        if self.has_rgb and mesh.vertices.shape[0]:
+            _, mesh.vertex_colors = self.compute_unbounded_tsdf(mesh.vertices, None, voxel_size, return_rgb=True)
+        return mesh
+
+
 def cameras_in_box(camera_centers, box):
     """Indices of the cameras whose centre lies inside a tile's box.txt rectangle [mx, Mx, my, My] -- the filter
     extract_mesh_split.py:58-67 applies before rendering a tile's views."""

@@ -130,3 +130,63 @@ def test_bounded_volume_extracts_its_mesh():
     torch.cuda.synchronize()
     org = np.array([-0.4, -0.3, 0.2], dtype=np.float32)
     _same(m.numpy(), mc.extract(f, w, 1.0, 0.0, org, np.float32(0.02), rgb))
+
+
+def test_marching_cubes_with_contraction_meshes_the_chunked_lattice_in_one_piece():
+    """mcube_utils.py:17-110 with two chunks per axis: the lattice is the reference's (shared chunk boundaries once), the
+    mesh equals the oracle's on the same samples, is closed across the chunk seams and points outwards."""
+    from gsr_b200.mesh import marching_cubes_with_contraction
+    from oracle import mcubes_oracle as mc
+    seen = []
+
+    def field(p):
+        return (p - torch.tensor([0.1, -0.05, 0.2], device=p.device)).norm(dim=-1) - 0.6 + 0.05 * torch.sin(9 * p[:, 0])
+
+    def sdf(p):
+        assert p.is_cuda and p.shape[1] == 3 and p.shape[0] <= 40_000
+        seen.append(p)
+        return field(p)
+
+    lo, hi = (-1.0, -0.9, -0.8), (0.9, 1.0, 1.1)
+    mesh = marching_cubes_with_contraction(sdf, resolution=64, bounding_box_min=lo, bounding_box_max=hi, crop=32, points_per_call=40_000)
+    pts = torch.cat(seen)
+    G = 2 * 31 + 1
+    assert pts.shape[0] == G ** 3
+    lattice = torch.cat([field(q) for q in seen]).reshape(G, G, G)
+    xs = pts.reshape(G, G, G, 3)[:, 0, 0, 0].cpu().numpy()
+    assert xs[0] == np.float32(lo[0]) and xs[-1] == np.float32(hi[0]) and (np.diff(xs) > 0).all()       # the seam sample once
+    ov, of, _ = mc.extract(lattice.cpu().numpy())
+    spacing = np.array([(hi[k] - lo[k]) / 2 / 31 for k in range(3)], dtype=np.float32)
+    want_v = ov[:, [2, 1, 0]] * spacing + np.array(lo, dtype=np.float32)
+    gv, gf, _ = mesh.numpy()
+    assert np.array_equal(gf, of[:, [0, 2, 1]]) and np.array_equal(gv, want_v.astype(np.float32))
+    assert all(u == [1, 1] for u in mc.edge_use_counts(gf).values())
+    p = gv[gf].astype(np.float64)
+    assert np.einsum("ij,ij->i", p[:, 0], np.cross(p[:, 1], p[:, 2])).sum() > 0
+    # the contraction hook and the clip
+    far = marching_cubes_with_contraction(field, resolution=64, bounding_box_min=lo, bounding_box_max=hi, crop=32,
+                                          inv_contraction=lambda v: v * 100.0, max_range=32.0)
+    assert float(far.vertices.abs().max()) == 32.0 and torch.equal(far.triangles, mesh.triangles)
+    empty = marching_cubes_with_contraction(lambda q: torch.ones(q.shape[0], device=q.device), resolution=32, crop=32)
+    assert empty.vertices.shape == (0, 3) and empty.triangles.shape == (0, 3)
+
+
+def test_extract_mesh_unbounded_runs_the_whole_chain():
+    """TSDFFusion.extract_mesh_unbounded (mesh_utils.py:181-277): contracted lattice -> fusion -> marching cubes -> colours."""
+    from gsr_b200.mesh import post_process_mesh
+    from gsr_b200.tsdf import TSDFFusion
+    from tsdf_synth import build_tsdf_case
+    c = build_tsdf_case("contracted", n=16)
+    f = TSDFFusion([torch.from_numpy(m) for m in c["projs"]], [torch.from_numpy(d) for d in c["depthmaps"]],
+                   [torch.from_numpy(r) for r in c["rgbmaps"]], center=c["center"], radius=c["radius"])
+    xyz = torch.from_numpy(c["center"]).cuda() + 0.5 * c["radius"] * torch.randn(5000, 3, device="cuda")
+    mesh = f.extract_mesh_unbounded(resolution=128, gaussians_xyz=xyz, crop=64)
+    V, F = mesh.vertices.shape[0], mesh.triangles.shape[0]
+    assert F > 1000 and mesh.vertex_colors.shape == (V, 3)
+    assert torch.isfinite(mesh.vertices).all() and float(mesh.vertex_colors.min()) >= 0.0 and float(mesh.vertex_colors.max()) <= 1.0 + 1e-6
+    assert int(mesh.triangles.min()) == 0 and int(mesh.triangles.max()) == V - 1
+    # vertices are the uncontracted lattice crossings: mapping them back gives tsdf ~ 0 there (on the [-1, 1] scale of the truncated field)
+    back = f.compute_unbounded_tsdf(f.contract_normalized(mesh.vertices), True, f.radius * 2 / 128)
+    assert float(back.abs().median()) < 0.2
+    post = post_process_mesh(mesh, cluster_to_keep=3)
+    assert 0 < post.triangles.shape[0] <= F
