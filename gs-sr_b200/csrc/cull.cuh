@@ -29,8 +29,13 @@ struct Quadric {           // q(x,y) = xx x^2 + 2 xy x y + yy y^2 + 2 bx x + 2 b
 };
 
 // tau (with slack) for an opacity; < 0 means the splat can never reach 1/255.
+// A NaN opacity is not "never": the reference's alpha = min(0.99f, opacity * G) is fminf, which drops the NaN, so such a
+// Gaussian blends with alpha 0.99 on every pixel of its rectangle (S/forward.cu:384, G/forward.cu:349).  TAU_ALWAYS tells
+// the callers to skip the culling for it.
+constexpr float TAU_ALWAYS = 3.0e38f;
 __device__ __forceinline__ float contribution_tau(float opacity) {
     float a = 255.0f * opacity;
+    if (a != a) return TAU_ALWAYS;
     if (!(a >= 1.0f)) return -1.0f;
     return 2.0f * __logf(a) * 1.001f + 2e-3f;
 }
@@ -101,6 +106,7 @@ __device__ __forceinline__ CullRec make_cull_rec(float3 Tu, float3 Tv, float3 Tw
     Quadric q = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (no_cull) { mode = CULL_ALWAYS; tau = fmaxf(tau, 0.f); }
     else if (tau < 0.f) { mode = CULL_NEVER; tau = 0.f; }
+    else if (tau == TAU_ALWAYS) mode = CULL_ALWAYS;
     else {
         const float3 tu = make_float3(fmaf(-sx, Tw.x, Tu.x), fmaf(-sx, Tw.y, Tu.y), fmaf(-sx, Tw.z, Tu.z));
         const float3 tv = make_float3(fmaf(-sy, Tw.x, Tv.x), fmaf(-sy, Tw.y, Tv.y), fmaf(-sy, Tw.z, Tv.z));

@@ -142,6 +142,10 @@ ewa_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D, const
         const float px = (float)((((double)(hx * p_w) + 1.0) * vc.W - 1.0) * 0.5);
         const float py = (float)((((double)(hy * p_w) + 1.0) * vc.H - 1.0) * 0.5);
         const int ri = (int)radius;
+        // A covariance that overflowed (scales ~1e18 and beyond) has a NaN radius -> 0.  The reference then still counts
+        // the one tile under the centre but writes no key for radii == 0 (G/rasterizer_impl.cu duplicateWithKeys): an
+        // uninitialised slot in its lists.  Here such a Gaussian is simply invisible.
+        if (ri <= 0) break;
         int x0, y0, x1, y1;
         get_rect(px, py, ri, vc.gx, vc.gy, x0, y0, x1, y1);
         if ((x1 - x0) * (y1 - y0) == 0) break;
@@ -159,6 +163,7 @@ ewa_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D, const
         Quadric q = {conic.x, conic.y, conic.z, 0.f, 0.f, 0.f};
         if (no_cull) { mode = CULL_ALWAYS; tau = fmaxf(tau, 0.f); }
         else if (tau < 0.f) { mode = CULL_NEVER; tau = 0.f; }
+        else if (tau == TAU_ALWAYS) mode = CULL_ALWAYS;
         else {
             const bool finite = fabsf(q.xx) < 3e38f && fabsf(q.yy) < 3e38f && fabsf(q.xy) < 3e38f &&
                                 fabsf(px) < 1e7f && fabsf(py) < 1e7f;

@@ -116,6 +116,14 @@ surfel_preprocess_fwd(int P, int D, int M, const float* __restrict__ means3D,
             Tw = make_float3(__ldg(t + 6), __ldg(t + 7), __ldg(t + 8));
             normal = make_float3(0.f, 0.f, 1.f);
         }
+        // Domain limit of the record form: the per-tile records hold the adjugate rows and det T of the tile-local T
+        // (~|T|^2, ~1e4 |T|^3), which must stay finite.  |T| ~ scale * focal + depth * pixel: ~1e5 in real scenes; beyond
+        // 1e10 (world scales ~1e7, or NaN / Inf parameters, which the reference drops at its rectangle test) the surfel
+        // is invisible here -- the reference still renders finite ones up to ~1e16.  Contained: no NaN reaches a pixel or
+        // another Gaussian's gradient.
+        const float tsum = fabsf(Tu.x) + fabsf(Tu.y) + fabsf(Tu.z) + fabsf(Tv.x) + fabsf(Tv.y) + fabsf(Tv.z) + fabsf(Tw.x) +
+                           fabsf(Tw.y) + fabsf(Tw.z);
+        if (!(tsum < 1e10f)) break;
         // DUAL_VISIABLE, S/forward.cu:209-214
         const float cosv = -dot_yxz(pv.x, normal.x, pv.y, normal.y, pv.z, normal.z);
         if (cosv == 0.f) break;
