@@ -420,8 +420,11 @@ def mesh_gather_check(rank, world, device):
                         [torch.from_numpy(c["rgbmaps"][i]) for i in idx])
     mine = [(2 * rank) % nv, (2 * rank + 1) % nv]                      # two views per tile
     vol = BoundedTSDFVolume(with_rgb=True, device=device, **grid).integrate(*pick(mine))
-    warm = torch.zeros(1 << 20, device=device)
-    torch.distributed.reduce(warm, 0)                                  # NCCL channel set-up is not part of the gather
+    warm = torch.zeros(128 ** 3, device=device)
+    for _ in range(2):
+        torch.distributed.reduce(warm, 0)                              # NCCL channel set-up is not part of the gather
+    from gsr_b200.mesh import extract_triangle_mesh, post_process_mesh
+    post_process_mesh(extract_triangle_mesh(torch.randn(32, 32, 32, device=device)), cluster_to_keep=5)   # module load, allocator
     torch.distributed.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -432,7 +435,6 @@ def mesh_gather_check(rank, world, device):
     every = [v for r in range(world) for v in ((2 * r) % nv, (2 * r + 1) % nv)]
     full = BoundedTSDFVolume(with_rgb=True, device=device, **grid).integrate(*pick(every))
     # ... and meshes the gathered volume where it lies (extract_mesh_split.py:119-128: extract_triangle_mesh + post_process_mesh)
-    from gsr_b200.mesh import post_process_mesh
     m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     m0.record()
     mesh = post_process_mesh(vol.extract_triangle_mesh(), cluster_to_keep=50)

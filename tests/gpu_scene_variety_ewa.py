@@ -1,15 +1,21 @@
-"""Developer helper (not a pytest): fwd+bwd time of the 3DGS rasterizer against the reference build on non-benchmark
-scenes (see gpu_scene_variety_time.py), incl. a thin depth shell and screen-filling splats."""
+"""Developer helper (not a pytest): fwd+bwd time of the 3DGS rasterizer (PLANE=1: the PGSR plane rasterizer with render_geo)
+against the reference build on non-benchmark scenes (see gpu_scene_variety_time.py), incl. a thin depth shell and
+screen-filling splats."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import harness as hz, synth
 import torch
 from oracle import refcuda
-from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+PLANE = os.environ.get("PLANE", "0") == "1"
+if PLANE:
+    from diff_plane_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+else:
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
 P, W, H = 1_000_000, 1600, 900
-gc, _ = synth.make_upstream_grads(W, H, seed=3, n_others=6, zero_from=6)
+gc, go = synth.make_upstream_grads(W, H, seed=3, n_others=6, zero_from=6)
 gct = torch.from_numpy(gc).cuda()
+gam, gpd = torch.from_numpy(np.ascontiguousarray(go[:5])).cuda(), torch.from_numpy(np.ascontiguousarray(go[5:6])).cuda()
 
 
 def ev(fn, n=6, warm=2):
@@ -41,22 +47,35 @@ def variants():
 
 for name, sc in variants():
     tt = hz.to_torch(sc)
-    rast = GaussianRasterizer(GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy,
-                                                            bg=tt["bg"], scale_modifier=1.0, viewmatrix=tt["view"], projmatrix=tt["proj"],
-                                                            sh_degree=0, campos=tt["campos"], prefiltered=False, debug=False))
+    kw = dict(image_height=H, image_width=W, tanfovx=sc.cam.tanfovx, tanfovy=sc.cam.tanfovy, bg=tt["bg"], scale_modifier=1.0,
+              viewmatrix=tt["view"], projmatrix=tt["proj"], sh_degree=0, campos=tt["campos"], prefiltered=False, debug=False)
+    if PLANE:
+        kw["render_geo"] = True
+    rast = GaussianRasterizer(GaussianRasterizationSettings(**kw))
+    am = torch.from_numpy(synth.make_all_map(sc)).cuda().requires_grad_(True) if PLANE else None
     leaves = {k: tt[k].clone().requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "colors")}
 
     def ours():
         for v in leaves.values(): v.grad = None
         m2d = torch.zeros_like(leaves["means3D"], requires_grad=True)
-        c, r = rast(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], colors_precomp=leaves["colors"],
-                    scales=leaves["scales"], rotations=leaves["rotations"])
-        torch.autograd.backward([c], [gct])
-    R = refcuda.RefGauss(plane=False)
+        common = dict(means3D=leaves["means3D"], means2D=m2d, opacities=leaves["opacities"], colors_precomp=leaves["colors"],
+                      scales=leaves["scales"], rotations=leaves["rotations"])
+        if PLANE:
+            am.grad = None
+            m2a = torch.zeros_like(leaves["means3D"], requires_grad=True)
+            c, r, ob, oam, pd = rast(means2D_abs=m2a, all_map=am, **common)
+            torch.autograd.backward([c, oam, pd], [gct, gam, gpd])
+        else:
+            c, r = rast(**common)
+            torch.autograd.backward([c], [gct])
+    R = refcuda.RefGauss(plane=PLANE)
 
     def ref():
         R.forward(tt["bg"], tt["view"], tt["proj"], tt["campos"], W, H, sc.cam.tanfovx, sc.cam.tanfovy, tt["means3D"], tt["opacities"],
-                  tt["scales"], tt["rotations"], colors=tt["colors"], all_map=None)
-        R.backward(gct)
+                  tt["scales"], tt["rotations"], colors=tt["colors"], all_map=am.detach() if PLANE else None)
+        if PLANE:
+            R.backward(gct, gam, gpd)
+        else:
+            R.backward(gct)
     a = ev(ours); b = ev(ref, 3, 1)
     print(f"{name:30s} ours {a:7.3f} ms  reference {b:7.3f} ms  x{b/a:.2f}", flush=True)
