@@ -164,7 +164,7 @@ def test_mesh_entry_points_argument_validation_without_gpu():
     nv, nt = C.c_longlong(0), C.c_longlong(0)
     assert L.gsr_mc_workspace_bytes(0, 4, 4) == 0
     ws = L.gsr_mc_workspace_bytes(512, 512, 512)
-    assert 3 * 512 ** 3 < ws < 3.1 * 512 ** 3                       # 1 + 2 bytes per voxel + counters
+    assert 3.25 * 512 ** 3 < ws < 3.3 * 512 ** 3                    # 1 + 2 bytes + 2 bits per voxel + counters
     assert L.gsr_mc_count(0, 4, 4, None, None, 0.0, 0.0, None, C.byref(nv), C.byref(nt), None) == -1
     assert L.gsr_mc_count(4, 4, 4, None, None, 0.0, 0.0, None, C.byref(nv), C.byref(nt), None) == -1      # tsdf required
     assert L.gsr_mc_count(2048, 2048, 2048, None, None, 0.0, 0.0, None, C.byref(nv), C.byref(nt), None) != 0

@@ -190,3 +190,24 @@ def test_extract_mesh_unbounded_runs_the_whole_chain():
     assert float(back.abs().median()) < 0.2
     post = post_process_mesh(mesh, cluster_to_keep=3)
     assert 0 < post.triangles.shape[0] <= F
+
+
+@pytest.mark.parametrize("name", ["noise", "observed"])
+def test_product_reproduces_the_frozen_conventions(name):
+    """The committed vectors of tests/golden/make_golden_mesh.py through the C ABI: mesh and cleaned mesh, bit for bit."""
+    import os
+    import sys
+    from gsr_b200.mesh import TriangleMesh, extract_triangle_mesh, post_process_mesh
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold_dir)
+    from make_golden_mesh import build
+    g = np.load(os.path.join(gold_dir, f"mesh_{name}.npz"))
+    c, f, w, rgb = build(name)
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    m = extract_triangle_mesh(t(f), t(w), 1.0 if w is not None else None, c["level"], c["origin"], c["voxel"], t(rgb))
+    v, faces, col = m.numpy()
+    assert np.array_equal(v, g["verts"]) and np.array_equal(faces, g["faces"])
+    pv, pf, pc = post_process_mesh(m, cluster_to_keep=2, min_triangles=4).numpy()
+    assert np.array_equal(pv, g["post_verts"]) and np.array_equal(pf, g["post_faces"])
+    if rgb is not None:
+        assert np.array_equal(col, g["colors"]) and np.array_equal(pc, g["post_colors"])

@@ -110,3 +110,23 @@ def test_generated_product_table_is_the_oracle_table():
             tri = [(words[case] >> (12 * t + 4 * k)) & 15 for k in range(3)]
             assert tri == [int(e) for e in mc.TABLE[case, 3 * t:3 * t + 3]]
         assert words[case] >> (12 * ntri[case]) == 0
+
+
+def test_oracles_reproduce_the_frozen_conventions():
+    """tests/golden/mesh_*.npz (make_golden_mesh.py): frozen outputs of the two restatements -- the reference has nothing
+    to pin them to (Open3D / skimage absent), so the repo's own conventions are pinned against drift."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_mesh import CASES, build
+    from oracle import mesh_clusters_oracle as mo
+    for name in CASES:
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"mesh_{name}.npz"))
+        assert np.array_equal(g["table"], mc.TABLE) and np.array_equal(g["ntri"], mc.NTRI)
+        c, f, w, rgb = build(name)
+        v, faces, col = mc.extract(f, w, 1.0 if w is not None else None, c["level"], c["origin"], c["voxel"], rgb)
+        assert np.array_equal(v, g["verts"]) and np.array_equal(faces, g["faces"])
+        _, troot, ntris, _ = mo.clusters(v, faces)
+        assert np.array_equal(troot, g["tri_root"]) and np.array_equal(ntris, g["root_ntris"])
+        pv, pf, pc = mo.post_process_mesh(v, faces, col, cluster_to_keep=2, min_triangles=4)
+        assert np.array_equal(pv, g["post_verts"]) and np.array_equal(pf, g["post_faces"])
+        if col is not None:
+            assert np.array_equal(col, g["colors"]) and np.array_equal(pc, g["post_colors"])
