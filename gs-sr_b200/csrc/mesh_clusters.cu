@@ -191,6 +191,21 @@ __global__ void keep_by_cluster_size(const int* __restrict__ tri_root, const uns
     keep[t] = (r >= 0 && root_ntris[r] >= min_triangles) ? 1 : 0;
 }
 
+// sizes of the clusters (the non-zero entries of root_ntris), in any order, appended behind a warp-aggregated counter
+__global__ void collect_cluster_sizes(const unsigned* __restrict__ root_ntris, unsigned nv, unsigned* __restrict__ sizes,
+                                      unsigned cap, unsigned* __restrict__ count) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned x = i < nv ? root_ntris[i] : 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, x != 0u);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+    if (x != 0u && pos < cap) sizes[pos] = x;
+}
+
 struct FilterWorkspace {
     uint8_t* vert_flag;    // nv
     uint8_t* tri_flag;     // nf
@@ -263,6 +278,29 @@ extern "C" int gsr_mesh_clusters(long long nverts, long long ntris, const float*
         set_error("gsr_mesh_clusters: %u triangles index vertices outside [0, %lld)", bad, nverts);
         return GSR_E_INVALID;
     }
+    return GSR_OK;
+}
+
+extern "C" int gsr_mesh_cluster_sizes(long long nverts, const unsigned int* root_ntris, unsigned int* sizes, long long capacity,
+                                      long long* nclusters, void* stream_v) {
+    using namespace gsr;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    if (int rc = check_sizes("gsr_mesh_cluster_sizes", nverts, 0)) return rc;
+    if (!nclusters || capacity < 1 || capacity > 0x7fffffffLL || !sizes || (nverts > 0 && !root_ntris)) {
+        set_error("gsr_mesh_cluster_sizes: invalid argument");
+        return GSR_E_INVALID;
+    }
+    *nclusters = 0;
+    if (nverts == 0) return GSR_OK;
+    // the counter lives in the last word of the caller's buffer
+    unsigned* count = sizes + (capacity - 1);
+    GSR_CUDA_CHECK(cudaMemsetAsync(count, 0, 4, s));
+    collect_cluster_sizes<<<((unsigned)nverts + 255) / 256, 256, 0, s>>>(root_ntris, (unsigned)nverts, sizes, (unsigned)(capacity - 1), count);
+    GSR_CUDA_CHECK(cudaGetLastError());
+    unsigned host_count = 0;
+    GSR_CUDA_CHECK(cudaMemcpyAsync(&host_count, count, 4, cudaMemcpyDeviceToHost, s));
+    GSR_CUDA_CHECK(cudaStreamSynchronize(s));
+    *nclusters = host_count;
     return GSR_OK;
 }
 

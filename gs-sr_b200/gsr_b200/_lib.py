@@ -93,6 +93,8 @@ def lib():
         _ll = C.c_longlong
         L.gsr_mesh_clusters.restype = C.c_int
         L.gsr_mesh_clusters.argtypes = [_ll, _ll] + [_fp] * 6 + [C.c_void_p]
+        L.gsr_mesh_cluster_sizes.restype = C.c_int
+        L.gsr_mesh_cluster_sizes.argtypes = [_ll, _fp, _fp, _ll, C.POINTER(_ll), C.c_void_p]
         L.gsr_mesh_keep_clusters.restype = C.c_int
         L.gsr_mesh_keep_clusters.argtypes = [_ll, _fp, _fp, C.c_uint, _fp, C.c_void_p]
         L.gsr_mesh_filter_workspace_bytes.restype = C.c_size_t

@@ -92,6 +92,24 @@ def _clusters(mesh, with_area):
 
 
 @torch.no_grad()
+def _cluster_sizes(root_ntris, capacity=1 << 16):
+    """The non-zero entries of root_ntris as a host array (gathered on the device: a few kB travel, not the whole array)."""
+    dev = root_ntris.device
+    nv = root_ntris.shape[0]
+    if nv == 0:
+        return np.zeros(0, dtype=np.int64)
+    n = ctypes.c_longlong(0)
+    while True:
+        buf = torch.empty(capacity, dtype=torch.int32, device=dev)
+        with on_device(dev):
+            check(lib().gsr_mesh_cluster_sizes(nv, root_ntris.data_ptr(), buf.data_ptr(), capacity, ctypes.byref(n),
+                                               stream_ptr(dev)), "gsr_mesh_cluster_sizes")
+        if n.value <= capacity - 1:
+            return buf[:n.value].cpu().numpy().astype(np.int64)
+        capacity = n.value + 2
+
+
+@torch.no_grad()
 def cluster_connected_triangles(mesh):
     """``mesh.cluster_connected_triangles()`` as the reference calls it (mesh_utils.py:34): (triangle_clusters (F,) int32
     device tensor, cluster_n_triangles (C,) numpy int64, cluster_area (C,) numpy float64).  Clusters are numbered by
@@ -142,8 +160,7 @@ def post_process_mesh(mesh, cluster_to_keep=1000, min_triangles=50):
     at least `min_triangles` triangles is kept."""
     dev = mesh.vertices.device
     _, troot, ntri, _ = _clusters(mesh, False)
-    sizes = ntri.cpu().numpy()
-    sizes = np.sort(sizes[sizes > 0])
+    sizes = np.sort(_cluster_sizes(ntri))
     n_cluster = int(sizes[-cluster_to_keep]) if sizes.shape[0] >= cluster_to_keep else 0
     n_cluster = max(n_cluster, int(min_triangles))
     nf = troot.shape[0]

@@ -340,6 +340,10 @@ int gsr_mc_emit(int nx, int ny, int nz, const float* tsdf, const float* rgb, flo
  *                           (0 at every other index; root_area and verts may both be NULL).  Triangles are joined through
  *                           shared vertices (Open3D: shared edges -- the same clusters unless two sheets touch in one point).
  *                           Synchronises `stream`; GSR_E_INVALID if a triangle indexes outside [0, nverts).
+ *   gsr_mesh_cluster_sizes  the cluster sizes (non-zero entries of root_ntris) gathered into sizes[0 .. nclusters), any order
+ *                           -- what the reference sorts on the host to find its N-th largest cluster (mesh_utils.py:39);
+ *                           `capacity` words, the last one is scratch; nclusters may exceed capacity - 1 (then only the
+ *                           first capacity - 1 were stored: call again with a larger buffer).  Synchronises `stream`.
  *   gsr_mesh_keep_clusters  keep[t] = root_ntris[tri_root[t]] >= min_triangles  (mesh_utils.py:42: the inverse of
  *                           triangles_to_remove).
  *   gsr_mesh_filter_count / gsr_mesh_filter_emit   drop the triangles with tri_keep[t] == 0, then the vertices no kept triangle
@@ -349,6 +353,8 @@ int gsr_mc_emit(int nx, int ny, int nz, const float* tsdf, const float* rgb, flo
  *                           gsr_mesh_filter_workspace_bytes(nverts, ntris) device bytes, 256-byte aligned, shared by the two. */
 int gsr_mesh_clusters(long long nverts, long long ntris, const float* verts, const int* faces, int* vertex_root, int* tri_root,
                       unsigned int* root_ntris, double* root_area, void* stream);
+int gsr_mesh_cluster_sizes(long long nverts, const unsigned int* root_ntris, unsigned int* sizes, long long capacity,
+                           long long* nclusters_host, void* stream);
 int gsr_mesh_keep_clusters(long long ntris, const int* tri_root, const unsigned int* root_ntris, unsigned int min_triangles,
                            unsigned char* tri_keep, void* stream);
 size_t gsr_mesh_filter_workspace_bytes(long long nverts, long long ntris);
