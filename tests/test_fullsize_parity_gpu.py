@@ -237,3 +237,31 @@ def test_cfg4_plane_matches_reference_build(view):
     assert dobs.sum() <= (mg[2] < BAND).sum() + flipped.size and np.abs(out["observe"] - ref["observe"]).max() <= 2
     check_grads(sc, out, ref, ("means3D", "means2D", "means2D_abs", "colors", "opacities", "scales", "rotations", "all_map"),
                 flipped, None, label)
+
+
+@pytest.mark.parametrize("kind", ["surfel", "gaussian"])
+def test_more_than_2_pow_23_gaussians_keep_their_indices(kind):
+    """P >= 2^23: the record word has no room left for the forward's "blended" marks next to the Gaussian index (bits 23-30),
+    so the marks are off and the backward falls back to its cull test.  Ids above 2^23 must come through the records intact:
+    compared with the reference build (radii, image, gradients) on 8.4 M small splats, the visible ones spread over the
+    whole index range."""
+    from oracle import refcuda
+    var = "surfel" if kind == "surfel" else "gaussian"
+    if not refcuda.available(var):
+        pytest.skip(f"oracle/_ref/libref_{var}.so did not travel")
+    P, W, H = (1 << 23) + 4097, 400, 304
+    sc = synth.make_scene(P, W, H, seed=77, sigma_px=0.8, scale_dims=2 if kind == "surfel" else 3)
+    gc, go = synth.make_upstream_grads(W, H, seed=78)
+    if kind == "surfel":
+        out, ref = hz.run_product_surfel(sc, gc, go), hz.run_refcuda_surfel(sc, gc, go)
+    else:
+        out, ref = hz.run_product_gauss(sc, gc), hz.run_refcuda_gauss(sc, gc)
+    assert np.array_equal(out["radii"], ref["radii"])
+    vis = np.nonzero(out["radii"] > 0)[0]
+    assert vis.max() >= (1 << 23) and vis.size > P // 2
+    assert hz.rel_linf(out["color"], ref["color"], 1e-4) <= 1e-4
+    for k in out["grads"]:
+        a, b = out["grads"][k], ref["grads"][k]
+        assert hz.rel_linf(a, b, 1e-4) <= 1e-3, k
+        hi = np.arange(a.shape[0]) >= (1 << 23)            # the rows only a 24-bit index reaches
+        assert np.abs(b[hi]).max() > 0 and hz.rel_linf(a[hi], b[hi], 1e-3) <= 1e-3, k
