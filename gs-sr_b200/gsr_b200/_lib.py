@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import os
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -141,7 +142,7 @@ def ptr(t):
 # ONCE per process (building a ctypes thunk costs more than the allocation it performs); the
 # `user` pointer carries the id of the TorchBuffers instance that serves the call.
 _ACTIVE = {}
-_NEXT_ID = [1]
+_NEXT_ID = itertools.count(1)      # next() is atomic under the GIL: two host threads never share an id
 
 
 def _make_cb(name):
@@ -166,8 +167,7 @@ class TorchBuffers:
         self._torch = torch
         self.device = device
         self.tensors = {}
-        self.user = _NEXT_ID[0]
-        _NEXT_ID[0] += 1
+        self.user = next(_NEXT_ID)
 
     def __enter__(self):
         _ACTIVE[self.user] = self
