@@ -189,12 +189,14 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                             T = test_T;
                             last_contrib = (uint32_t)(b * RBATCH + j + 1);
                         }
-                        if (__all_sync(FULLMASK, done)) { warp_done = true; break; }
                     }
                 }
                 if (mark_plane != nullptr && ((used >> lane) & 1u))
                     atomicOr(reinterpret_cast<uint32_t*>(mark_plane + range_x + b * RBATCH + c0 + lane) + 3,
                              1u << (REC_USED_SHIFT + warp));
+                // one exit vote per chunk instead of one per survivor (as in surfel_render_fwd): a warp that finishes inside a
+                // chunk skips the chunk's remaining survivors at the any-vote above
+                warp_done = __all_sync(FULLMASK, done);
             }
         }
         const int all_done = __syncthreads_and(warp_done);
