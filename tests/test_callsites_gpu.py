@@ -5,7 +5,6 @@ import importlib
 import json
 import os
 
-import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")

@@ -197,7 +197,7 @@ def test_product_reproduces_the_frozen_conventions(name):
     """The committed vectors of tests/golden/make_golden_mesh.py through the C ABI: mesh and cleaned mesh, bit for bit."""
     import os
     import sys
-    from gsr_b200.mesh import TriangleMesh, extract_triangle_mesh, post_process_mesh
+    from gsr_b200.mesh import extract_triangle_mesh, post_process_mesh
     gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     sys.path.insert(0, gold_dir)
     from make_golden_mesh import build
