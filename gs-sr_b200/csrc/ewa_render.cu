@@ -96,9 +96,6 @@ __device__ __forceinline__ EwaEval ewa_eval(float4 p0, float4 p1, float fx, floa
 }
 
 // ---- forward ------------------------------------------------------------------------------------
-#ifndef GSR_EWA_FWD_PAIR2
-#define GSR_EWA_FWD_PAIR2 0        // survivors two at a time: +2 % on the surfel forward, -2 % here (1.540 -> 1.572 ms at 1 M)
-#endif
 template <bool GEO>
 __global__ void __launch_bounds__(TILE_PIX)
 ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restrict__ planes, size_t pstride, int W, int H,
@@ -159,7 +156,12 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                 if (e < cnt) hit = ewa_entry_hits_block(sb[0][e], sb[1][e], bx0, bx1, by0, by1);
                 uint32_t m = __ballot_sync(FULLMASK, hit);
                 uint32_t used = 0;
-                auto blend = [&](const EwaEval& ev, int bitpos, int j, float idx_word) {
+                while (m) {
+                    const int bitpos = __ffs(m) - 1;
+                    const int j = c0 + bitpos;
+                    m &= m - 1;
+                    const float4 p0 = sb[0][j], p1 = sb[1][j];
+                    const EwaEval ev = ewa_eval(p0, p1, fx, fy);
                     bool valid = ev.valid && !done;
                     if (__any_sync(FULLMASK, valid)) {
                         const float test_T = T * (1.0f - ev.alpha);
@@ -181,39 +183,14 @@ ewa_render_fwd(const uint32_t* __restrict__ tile_offset, const float4* __restric
                         if (out_observe != nullptr) {   // L/forward.cu:381-384, T before the update
                             const uint32_t ob = __ballot_sync(FULLMASK, valid && T > 0.5f);
                             if (ob != 0u && lane == 0)
-                                atomicAdd(out_observe + (__float_as_uint(idx_word) & idx_mask), __popc(ob));
+                                atomicAdd(out_observe + (__float_as_uint(p1.w) & idx_mask), __popc(ob));
                         }
                         if (valid) {
                             T = test_T;
                             last_contrib = (uint32_t)(b * RBATCH + j + 1);
                         }
                     }
-                };
-#if GSR_EWA_FWD_PAIR2
-                // survivors two at a time (as in surfel_render_fwd): the two evaluations are independent chains ending in a
-                // MUFU.EX2, interleaved they hide each other's latency; the blends follow in list order
-                while (m) {
-                    const int b1 = __ffs(m) - 1;
-                    m &= m - 1;
-                    const bool two = m != 0u;
-                    const int b2 = two ? __ffs(m) - 1 : b1;
-                    m &= m - 1;
-                    const int j1 = c0 + b1, j2 = c0 + b2;
-                    const float4 q0 = sb[0][j1], q1 = sb[1][j1], r0 = sb[0][j2], r1 = sb[1][j2];
-                    const EwaEval e1 = ewa_eval(q0, q1, fx, fy);
-                    const EwaEval e2 = ewa_eval(r0, r1, fx, fy);
-                    blend(e1, b1, j1, q1.w);
-                    if (two) blend(e2, b2, j2, r1.w);
                 }
-#else
-                while (m) {
-                    const int bitpos = __ffs(m) - 1;
-                    const int j = c0 + bitpos;
-                    m &= m - 1;
-                    const float4 p0 = sb[0][j], p1 = sb[1][j];
-                    blend(ewa_eval(p0, p1, fx, fy), bitpos, j, p1.w);
-                }
-#endif
                 if (mark_plane != nullptr && ((used >> lane) & 1u))
                     atomicOr(reinterpret_cast<uint32_t*>(mark_plane + range_x + b * RBATCH + c0 + lane) + 3,
                              1u << (REC_USED_SHIFT + warp));
