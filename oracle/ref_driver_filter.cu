@@ -16,26 +16,30 @@ extern "C" int ref_visible_filter(int P, int W, int H, const float* means3D, con
                                   const float* viewmatrix, const float* projmatrix, float tan_fovx,
                                   float tan_fovy, int prefiltered, int* radii, int debug) {
     if (P == 0) return 0;
-    char *g = nullptr, *b = nullptr, *i = nullptr;
-    auto mk = [](char** slot) {
-        return std::function<char*(size_t)>([slot](size_t n) {
-            if (*slot) cudaFree(*slot);
-            *slot = nullptr;
-            cudaMalloc(slot, n + 256);
-            return *slot;
+    // Scratch as the reference's torch glue provides it: tensors resized through torch's caching allocator, i.e. no
+    // cudaMalloc / cudaFree and no synchronisation per call.  Grow-only static buffers stand in for the allocator (a
+    // cudaMalloc + cudaFree per call would be this driver's cost, not the reference's: it made the reference arm of
+    // bench.py's visible_filter entry 1.2 - 95 ms depending on the box).
+    static char* slots[3] = {nullptr, nullptr, nullptr};
+    static size_t caps[3] = {0, 0, 0};
+    auto mk = [](int k) {
+        return std::function<char*(size_t)>([k](size_t n) {
+            if (n + 256 > caps[k]) {
+                if (slots[k]) cudaFree(slots[k]);
+                slots[k] = nullptr;
+                caps[k] = 0;
+                if (cudaMalloc(&slots[k], n + 256) == cudaSuccess) caps[k] = n + 256;
+            }
+            return slots[k];
         });
     };
     int rc = 0;
     try {
-        CudaRasterizer::Rasterizer::visible_filter(mk(&g), mk(&b), mk(&i), P, 0, W, H, means3D, scales,
+        CudaRasterizer::Rasterizer::visible_filter(mk(0), mk(1), mk(2), P, 0, W, H, means3D, scales,
                                                    scale_modifier, rotations, cov3D_precomp, viewmatrix,
                                                    projmatrix, tan_fovx, tan_fovy, prefiltered != 0, radii,
                                                    debug != 0);
-        cudaDeviceSynchronize();
-        rc = (int)cudaGetLastError();
+        rc = (int)cudaGetLastError();          // launch errors; the caller synchronises when it reads the result
     } catch (...) { rc = -1; }
-    if (g) cudaFree(g);
-    if (b) cudaFree(b);
-    if (i) cudaFree(i);
     return rc;
 }

@@ -185,7 +185,7 @@ def ref_visible_filter(means3D, scales, rotations, view, proj, W, H, tanfovx, ta
     L = _LIBS.setdefault("filter", C.CDLL(path))
     P = means3D.shape[0]
     radii = torch.zeros((P,), dtype=torch.int32, device=means3D.device)
-    torch.cuda.synchronize()
+    # no synchronisation: the reference kernels launch on the legacy default stream, which is torch's default stream
     rc = L.ref_visible_filter(C.c_int(P), C.c_int(W), C.c_int(H), _p(means3D), _p(scales), C.c_float(scale_modifier),
                               _p(rotations), _p(cov3D_precomp), _p(view), _p(proj), C.c_float(tanfovx),
                               C.c_float(tanfovy), C.c_int(int(prefiltered)), _p(radii), C.c_int(0))
