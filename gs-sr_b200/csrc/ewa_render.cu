@@ -88,7 +88,13 @@ __device__ __forceinline__ EwaEval ewa_eval(float4 p0, float4 p1, float fx, floa
     EwaEval e;
     e.dx = p0.x - fx;
     e.dy = p0.y - fy;
-    const float power = -0.5f * (p0.z * e.dx * e.dx + p1.x * e.dy * e.dy) - p0.w * e.dx * e.dy;
+    // the operation sequence nvcc emits for the reference's  -0.5f * (a dx dx + c dy dy) - b dx dy  (G/forward.cu:339, read
+    // off oracle/_ref/libref_gaussian.so): fma(dx, dx a, dy (dy c)) ; fma(that, -0.5, -(dy (dx b))).  Spelled out so that
+    // `power` -- and with it the power > 0 test -- is bit-identical to the reference whatever code surrounds this function
+    // (left to the compiler, a refactoring of the forward changed the contraction and moved an Octree-PGSR iteration's
+    // agreement with the reference kernels from 4.8e-4 to 1.1e-3).  dx, dy are exact in both (tile-local vs global pixels).
+    const float quad = __fmaf_rn(e.dx, __fmul_rn(e.dx, p0.z), __fmul_rn(e.dy, __fmul_rn(e.dy, p1.x)));
+    const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(e.dy, __fmul_rn(e.dx, p0.w)));
     e.G = fast_ex2(power * LOG2E);
     e.alpha = fminf(ALPHA_MAX, p1.y * e.G);
     e.valid = !(power > 0.0f) && !(e.alpha < ALPHA_MIN);
