@@ -37,7 +37,7 @@ def dist2_knn3_cpu(points, candidates=8):
         raise ValueError("dist2_knn3_cpu needs at least 4 points (3 neighbours per point)")
     k = min(max(candidates, 4), P)
     tree = cKDTree(pts.astype(np.float64))
-    _, idx = tree.query(pts.astype(np.float64), k=k)
+    _, idx = tree.query(pts.astype(np.float64), k=k, workers=-1)      # all host cores; per-point results do not depend on it
     d2 = _d2_f32(pts[:, None, :], pts[idx])                         # (P,k) float32, GPU arithmetic
     # drop the query point itself: its own index when the tree returned it, else (more than k coincident points) any zero
     is_self = idx == np.arange(P)[:, None]
